@@ -1,0 +1,240 @@
+"""ctypes mirror of the C interface of libdeflate_b200.so.
+
+Two layers, as in the C code:
+  * the reference's own API (include/deflate_ext.h; reference:
+    src/include/deflate_ext.h:10-17): deflate_compress(fd_in, fd_out, fd_stats,
+    sw, ops), deflate_decompress(...)
+  * the thin CUDA C-ABI beneath it (include/deflate_b200.h): Compressor
+
+No CPU fallback: if the CUDA library is missing or no B200 is visible, the calls
+raise DflError."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(PKG, "libdeflate_b200.so")
+_lib = None
+
+
+class DflError(RuntimeError):
+    def __init__(self, code: int, what: str = ""):
+        self.code = code
+        msg = lib().dfl_b200_strerror(code).decode() if _lib is not None else ""
+        super().__init__(f"{what}: error {code} ({msg})")
+
+
+class DflParams(C.Structure):
+    _fields_ = [
+        ("window", C.c_int32),
+        ("seg_bytes", C.c_int32),
+        ("chain_limit", C.c_int32),
+        ("use_dict", C.c_int32),
+        ("block_mode", C.c_int32),
+    ]
+
+
+class DflSegInfo(C.Structure):
+    _fields_ = [
+        ("btype", C.c_int32),
+        ("ntokens", C.c_int32),
+        ("block_bits", C.c_int64),
+        ("out_bytes", C.c_int64),
+        ("out_offset", C.c_int64),
+    ]
+
+
+class StringLen(C.Structure):
+    _fields_ = [("str", C.POINTER(C.c_ubyte)), ("len", C.c_size_t)]
+
+
+def lib_path() -> str:
+    return _LIB
+
+
+def build(force: bool = False) -> None:
+    """Compile libdeflate_b200.so + zencode in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
+    if force or not os.path.exists(_LIB):
+        subprocess.run(["make", "-C", os.path.join(PKG, "csrc"), "-s"], check=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            raise OSError(f"{_LIB} is missing: run deflate_compression_b200.build() (there is no CPU fallback)")
+        L = C.CDLL(_LIB)
+        vp = C.c_void_p
+        L.dfl_b200_default_params.argtypes = [C.POINTER(DflParams)]
+        L.dfl_b200_strerror.restype = C.c_char_p
+        L.dfl_b200_strerror.argtypes = [C.c_int]
+        L.dfl_b200_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(DflParams)]
+        L.dfl_b200_destroy.argtypes = [vp]
+        L.dfl_b200_set_params.argtypes = [vp, C.POINTER(DflParams)]
+        L.dfl_b200_bound.restype = C.c_size_t
+        L.dfl_b200_bound.argtypes = [C.POINTER(DflParams), C.c_size_t]
+        L.dfl_b200_deflate_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t,
+                                              C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), vp]
+        L.dfl_b200_deflate_enqueue.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, C.c_size_t, vp]
+        L.dfl_b200_deflate_finish.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), vp]
+        L.dfl_b200_compress_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dfl_b200_keep_tokens.argtypes = [vp, C.c_int]
+        L.dfl_b200_num_segments.restype = C.c_long
+        L.dfl_b200_num_segments.argtypes = [vp]
+        L.dfl_b200_seg_info.argtypes = [vp, C.c_long, C.POINTER(DflSegInfo)]
+        L.dfl_b200_tokens.restype = C.c_long
+        L.dfl_b200_tokens.argtypes = [vp, C.c_long, vp, C.c_long]
+        L.dfl_b200_kernel_launches.restype = C.c_long
+        L.dfl_b200_kernel_launches.argtypes = [vp]
+        L.dfl_b200_enable_timing.argtypes = [vp, C.c_int]
+        L.dfl_b200_num_kernels.restype = C.c_int
+        L.dfl_b200_kernel_name.restype = C.c_char_p
+        L.dfl_b200_kernel_name.argtypes = [C.c_int]
+        L.dfl_b200_kernel_ms.restype = C.c_double
+        L.dfl_b200_kernel_ms.argtypes = [vp, C.c_int]
+        L.dfl_b200_synth_random.argtypes = [vp, C.c_size_t, C.c_uint64, vp]
+        # reference API (include/deflate_ext.h)
+        L.deflate_compress.restype = C.c_int
+        L.deflate_compress.argtypes = [C.c_int, C.c_int, C.c_int, C.c_ushort, C.c_int]
+        L.deflate_decompress.restype = C.c_int
+        L.deflate_decompress.argtypes = [C.POINTER(StringLen), C.POINTER(StringLen), C.c_int]
+        L.spawn_deflate_compr_t.restype = vp
+        L.deflate_compr_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_ushort]
+        L.deflate_compr_deinit.argtypes = [vp]
+        # synthetic corpora (host)
+        L.dfl_synth_random.argtypes = [vp, C.c_size_t, C.c_uint64]
+        L.dfl_synth_markov.argtypes = [vp, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint32]
+        L.dfl_synth_log.argtypes = [vp, C.c_size_t, C.c_uint64, vp, C.c_size_t]
+        L.dfl_synth_png.argtypes = [vp, C.c_size_t, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+class Compressor:
+    """One dfl_ctx (include/deflate_b200.h) bound to a CUDA device."""
+
+    def __init__(self, device: int = 0, window: int = 32768, seg_bytes: int = 32768, chain_limit: int = 0,
+                 use_dict: int = 1, block_mode: int = 0):
+        self.params = DflParams(window, seg_bytes, chain_limit, use_dict, block_mode)
+        self._ctx = C.c_void_p()
+        rc = lib().dfl_b200_create(C.byref(self._ctx), device, C.byref(self.params))
+        if rc:
+            self._ctx = C.c_void_p()
+            raise DflError(rc, "dfl_b200_create")
+
+    def close(self) -> None:
+        if self._ctx:
+            lib().dfl_b200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bound(self, n: int) -> int:
+        return int(lib().dfl_b200_bound(C.byref(self.params), n))
+
+    # ---- host buffers: complete zlib stream, H2D + D2H inside ----
+    def compress(self, data) -> bytes:
+        a = _u8(data)
+        cap = self.bound(a.size) + 16
+        out = np.empty(cap, dtype=np.uint8)
+        n = self.compress_into(a.ctypes.data, a.size, out.ctypes.data, cap)
+        return out[:n].tobytes()
+
+    def compress_into(self, in_ptr: int, n: int, out_ptr: int, cap: int) -> int:
+        out_len = C.c_size_t(0)
+        rc = lib().dfl_b200_compress_host(self._ctx, in_ptr, n, out_ptr, cap, C.byref(out_len))
+        if rc:
+            raise DflError(rc, "dfl_b200_compress_host")
+        return int(out_len.value)
+
+    # ---- device buffers: raw deflate body ----
+    def deflate_device(self, d_in: int, n: int, hist_len: int, is_final: bool, d_out: int, cap: int,
+                       stream: int = 0):
+        out_len = C.c_size_t(0)
+        adler = C.c_uint32(0)
+        rc = lib().dfl_b200_deflate_device(self._ctx, d_in, n, hist_len, int(is_final), d_out, cap,
+                                           C.byref(out_len), C.byref(adler), stream)
+        if rc:
+            raise DflError(rc, "dfl_b200_deflate_device")
+        return int(out_len.value), int(adler.value)
+
+    def enqueue(self, d_in: int, n: int, hist_len: int, is_final: bool, d_out: int, cap: int, stream: int = 0):
+        rc = lib().dfl_b200_deflate_enqueue(self._ctx, d_in, n, hist_len, int(is_final), d_out, cap, stream)
+        if rc:
+            raise DflError(rc, "dfl_b200_deflate_enqueue")
+
+    def finish(self, stream: int = 0):
+        out_len = C.c_size_t(0)
+        adler = C.c_uint32(0)
+        rc = lib().dfl_b200_deflate_finish(self._ctx, C.byref(out_len), C.byref(adler), stream)
+        if rc:
+            raise DflError(rc, "dfl_b200_deflate_finish")
+        return int(out_len.value), int(adler.value)
+
+    # ---- parity / stats ----
+    def keep_tokens(self, enable: bool = True) -> None:
+        lib().dfl_b200_keep_tokens(self._ctx, int(enable))
+
+    def num_segments(self) -> int:
+        return int(lib().dfl_b200_num_segments(self._ctx))
+
+    def seg_info(self, seg: int) -> DflSegInfo:
+        info = DflSegInfo()
+        rc = lib().dfl_b200_seg_info(self._ctx, seg, C.byref(info))
+        if rc:
+            raise DflError(rc, "dfl_b200_seg_info")
+        return info
+
+    def tokens(self, seg: int) -> np.ndarray:
+        nt = lib().dfl_b200_tokens(self._ctx, seg, None, 0)
+        if nt < 0:
+            raise DflError(int(nt), "dfl_b200_tokens")
+        out = np.empty(max(nt, 1), dtype=np.uint32)
+        lib().dfl_b200_tokens(self._ctx, seg, out.ctypes.data, nt)
+        return out[:nt]
+
+    # ---- measurement ----
+    def enable_timing(self, enable: bool = True) -> None:
+        lib().dfl_b200_enable_timing(self._ctx, int(enable))
+
+    def kernel_ms(self) -> dict:
+        L = lib()
+        return {L.dfl_b200_kernel_name(k).decode(): float(L.dfl_b200_kernel_ms(self._ctx, k))
+                for k in range(L.dfl_b200_num_kernels())}
+
+    def kernel_launches(self) -> int:
+        return int(lib().dfl_b200_kernel_launches(self._ctx))
+
+
+def deflate_compress(fd_in: int, fd_out: int, fd_stats: int = -1, sw: int = 32768, ops: int = 0) -> int:
+    """The reference entry point (src/include/deflate_ext.h:17): 0 or a negative error."""
+    return int(lib().deflate_compress(fd_in, fd_out, fd_stats, sw, ops))
+
+
+def deflate_decompress(comp, ops: int = 0) -> bytes:
+    """The reference entry point (src/include/deflate_ext.h:16) over a bytes object."""
+    a = _u8(comp)
+    src = StringLen(a.ctypes.data_as(C.POINTER(C.c_ubyte)), a.size)
+    dst = StringLen()
+    rc = lib().deflate_decompress(C.byref(dst), C.byref(src), ops)
+    if rc < 0:
+        raise DflError(rc, "deflate_decompress")
+    try:
+        return C.string_at(dst.str, dst.len) if dst.len else b""
+    finally:
+        if dst.str:
+            C.CDLL(None).free(dst.str)

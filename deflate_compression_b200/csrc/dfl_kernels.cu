@@ -1,0 +1,1375 @@
+/*
+ * dfl_kernels.cu -- sm_100a DEFLATE compress kernels + the thin C-ABI
+ * (include/deflate_b200.h).  B200-native replacement for the hot path of
+ * mparker97/deflate_compression: process_loop() in src/deflate_compress.c:219-347
+ * (hash-chain match search, greedy parse) and the Huffman accounting of
+ * src/h_tree.c:75-302, completed with the encode side the reference leaves as
+ * TODOs (src/deflate_compress.c:269,:279).
+ *
+ * Pipeline, per chunk of <= DFL_CHUNK_BYTES input (all on one stream, no host sync):
+ *   k_match : one CTA per segment.  [window | segment] staged into shared memory
+ *             with TMA bulk copies; one warp links every position into its hash
+ *             bucket chain (16-bit backward deltas); all warps then find, for
+ *             every position of the segment, the longest / nearest match by
+ *             walking the chain newest -> oldest (persistent lanes, refilled from
+ *             a block-wide counter).  Also the segment's Adler-32 partial sums.
+ *   k_parse : one warp per segment; greedy resolution of the per-position
+ *             candidates into the token stream (in place), lit/len + dist
+ *             histograms with shared-memory atomics.
+ *   k_huff  : one warp per segment; length-limited code lengths (15/15/7),
+ *             canonical codes, RFC 1951 3.2.7 header, exact stored/fixed/dynamic
+ *             cost and choice.
+ *   k_scan  : exclusive scan of segment sizes -> byte offsets in the stream.
+ *   k_emit  : one CTA per segment; prefix-sum bit packer, 128-bit stores.
+ * No tensor cores: nothing here is a dense contraction.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "deflate_b200.h"
+
+#define FULL 0xFFFFFFFFu
+#define NLL 286
+#define ND 30
+#define NCL 19
+#define LLS 288          /* stride of per-segment lit/len tables */
+#define DS 32            /* stride of per-segment distance tables */
+#define HDR_WORDS 160    /* 640 B >= 3+14+57+316*14 bits */
+#define NPOS_MAX 65536
+#define HASH_SIZE (1 << DFL_HASH_BITS)
+#define MATCH_THREADS 1024
+#define REFILL_MIN_IDLE 8
+#define DFL_CHUNK_BYTES (256u << 20)
+#define ADLER_MOD 65521u
+
+enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_NUM };
+static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final"};
+
+struct DevState {
+    unsigned long long total_out;  /* bytes of deflate body written so far */
+    unsigned long long adl_a;      /* sum of per-segment byte sums (mod 65521 each) */
+    unsigned long long adl_b;      /* sum of per-segment weighted sums */
+    unsigned int error;            /* 1 = output overflow */
+    unsigned int adler;            /* final Adler-32 */
+};
+
+struct SegArrays {
+    uint32_t *ll_freq;   /* [nseg][LLS] */
+    uint32_t *d_freq;    /* [nseg][DS] */
+    uint32_t *ntok;      /* [nseg] */
+    uint32_t *extra;     /* [nseg] sum of length/distance extra bits */
+    uint32_t *lltab;     /* [nseg][LLS]  code_rev | len << 16 of the chosen block type */
+    uint32_t *dtab;      /* [nseg][DS] */
+    uint32_t *hdr;       /* [nseg][HDR_WORDS] packed block header bits */
+    uint32_t *hdr_bits;  /* [nseg] */
+    uint32_t *btype;     /* [nseg] */
+    uint32_t *out_bytes; /* [nseg] */
+    unsigned long long *block_bits; /* [nseg] */
+    unsigned long long *out_off;    /* [nseg] */
+};
+
+/* ------------------------------------------------------------------------- */
+/* small device helpers                                                      */
+/* ------------------------------------------------------------------------- */
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+/* unaligned little-endian 4-byte load from a word-aligned shared array */
+__device__ __forceinline__ uint32_t ld4(const uint32_t *w, uint32_t byte_idx)
+{
+    uint32_t i = byte_idx >> 2;
+    uint32_t lo = w[i], hi = w[i + 1];
+    return __funnelshift_r(lo, hi, (byte_idx & 3) * 8);
+}
+
+/* RFC 1951 3.2.5: length 3..258 -> symbol 257..285 (same numbers as
+ * get_len_code, src/deflate_compress.c:182-200; extra bits per the RFC). */
+__device__ __forceinline__ int len_sym(int len, int &eb, int &ev)
+{
+    int t = len - 3;
+    if (len == 258) { eb = 0; ev = 0; return 285; }
+    if (t < 8) { eb = 0; ev = 0; return 257 + t; }
+    int k = 31 - __clz(t);
+    eb = k - 2;
+    ev = t & ((1 << eb) - 1);
+    return 261 + 4 * eb + ((t >> eb) & 3);
+}
+
+/* distance 1..32768 -> symbol 0..29 (get_dist_code, src/deflate_compress.c:202-217) */
+__device__ __forceinline__ int dist_sym(int dist, int &eb, int &ev)
+{
+    int t = dist - 1;
+    if (t < 4) { eb = 0; ev = 0; return t; }
+    int k = 31 - __clz(t);
+    eb = k - 1;
+    ev = t & ((1 << eb) - 1);
+    return 2 * k + ((t >> eb) & 1);
+}
+
+__device__ __forceinline__ int fixed_ll_len(int s) { return s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8; }
+
+/* mbarrier + TMA bulk copy (global -> shared), sm_90+ PTX */
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src_gmem), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_match                                                                   */
+/* ------------------------------------------------------------------------- */
+
+struct MatchSmem {
+    uint32_t data[(NPOS_MAX + 64) / 4]; /* [window | segment] bytes, 16 B of slack either side */
+    uint16_t delta[NPOS_MAX];           /* distance to the previous position of the same bucket, 0 = none */
+    uint16_t head[HASH_SIZE];           /* newest position of each bucket, 0xFFFF = empty */
+    uint64_t bar;
+    int next_pos;
+    uint32_t red_a[32];
+    unsigned long long red_b[32];
+};
+
+/*
+ * One CTA per segment.  For every position p of the segment computes the
+ * candidate token the greedy parse would emit if p were a parse head:
+ *   M(p) = longest match among q in [max(lo, p - window), p - 1], ties -> nearest,
+ *          capped at min(258, seg_hi - p); a literal if that is < 3.
+ * This is process_loop's chain walk (src/deflate_compress.c:244-263) and
+ * check_dup_str (:164-180) evaluated for all positions at once: because every
+ * position enters the index (:313-318) and chains are walked to the end (:249),
+ * M(p) is a pure function of the bytes.
+ */
+__global__ void __launch_bounds__(MATCH_THREADS, 1)
+k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, long long seg0,
+        dfl_params prm, uint32_t *__restrict__ tokcand, DevState *state)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MatchSmem &S = *reinterpret_cast<MatchSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long seg = seg0 + blockIdx.x;
+    const long long seg_lo = seg * prm.seg_bytes;
+    const long long seg_hi = (seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n;
+    const int seglen = (int)(seg_hi - seg_lo);
+    long long hist_lo = seg_lo;
+    if (prm.use_dict) {
+        hist_lo = seg_lo - prm.window;
+        if (hist_lo < -avail_hist) hist_lo = -avail_hist;
+    }
+    const int hist = (int)(seg_lo - hist_lo);
+    const int npos = hist + seglen;
+    const uint8_t *g0 = d_in + hist_lo;
+    const uint32_t soff = 16 + (uint32_t)((uintptr_t)g0 & 15); /* data byte i lives at smem byte soff + i */
+    uint8_t *sd = reinterpret_cast<uint8_t *>(S.data);
+
+    /* ---- stage [window | segment] into shared memory ---- */
+    {
+        int head_n = (int)((16 - ((uintptr_t)g0 & 15)) & 15);
+        if (head_n > npos) head_n = npos;
+        int bulk_n = (npos - head_n) & ~15;
+        int tail0 = head_n + bulk_n;
+        if (tid == 0) {
+            mbar_init(&S.bar, 1);
+            S.next_pos = 0;
+        }
+        for (int i = tid; i < HASH_SIZE / 2; i += MATCH_THREADS) reinterpret_cast<uint32_t *>(S.head)[i] = 0xFFFFFFFFu;
+        if (tid < 4) S.data[tid] = 0;
+        __syncthreads();
+        if (tid == 0 && bulk_n > 0) {
+            mbar_expect_tx(&S.bar, (uint32_t)bulk_n);
+            for (int o = 0; o < bulk_n; o += 16384) {
+                int c = bulk_n - o < 16384 ? bulk_n - o : 16384;
+                tma_bulk_g2s(sd + soff + head_n + o, g0 + head_n + o, (uint32_t)c, &S.bar);
+            }
+        }
+        if (tid < head_n) sd[soff + tid] = g0[tid];
+        for (int i = tail0 + tid; i < npos; i += MATCH_THREADS) sd[soff + i] = g0[i];
+        /* zero slack after the data so that over-reads compare unequal-or-zero deterministically */
+        if (tid < 32) sd[soff + npos + tid] = 0;
+        if (bulk_n > 0) mbar_wait(&S.bar, 0);
+        __syncthreads();
+    }
+
+    /* ---- Adler-32 partial sums of the segment bytes ---- */
+    {
+        uint32_t a = 0;
+        unsigned long long b = 0;
+        for (int i = tid; i < seglen; i += MATCH_THREADS) {
+            uint32_t v = sd[soff + hist + i];
+            a += v;
+            b += (unsigned long long)v * (uint32_t)(seglen - i);
+        }
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(FULL, a, o);
+            b += __shfl_xor_sync(FULL, b, o);
+        }
+        if (lane == 0) { S.red_a[warp] = a; S.red_b[warp] = b; }
+        __syncthreads();
+        if (warp == 0) {
+            a = S.red_a[lane];
+            b = S.red_b[lane];
+            for (int o = 16; o; o >>= 1) {
+                a += __shfl_xor_sync(FULL, a, o);
+                b += __shfl_xor_sync(FULL, b, o);
+            }
+            if (lane == 0) {
+                /* s1 += A ; s2 += B + A * (bytes after this segment)   (mod 65521) */
+                unsigned long long am = a % ADLER_MOD;
+                unsigned long long rest = (unsigned long long)(n - seg_hi) % ADLER_MOD;
+                unsigned long long bm = (b % ADLER_MOD + am * rest) % ADLER_MOD;
+                atomicAdd(&state->adl_a, am);
+                atomicAdd(&state->adl_b, bm);
+            }
+        }
+    }
+
+    /* ---- link every position into its bucket chain (one warp, position order) ----
+     * Same structure as the reference's dup_ht / dup_entries (src/deflate_compress.c:
+     * 64-67, :313-318), with backward deltas instead of ring indices. */
+    if (warp == 0) {
+        const int last = npos - 3; /* positions with 3 bytes available */
+        for (int base = 0; base <= last; base += 32) {
+            int p = base + lane;
+            bool valid = p <= last;
+            uint32_t h = valid ? DFL_HASH3(ld4(S.data, soff + p)) : (0x80000000u | lane);
+            uint32_t grp = __match_any_sync(FULL, h);
+            uint32_t lower = grp & lanemask_lt();
+            uint32_t prev = 0xFFFFu;
+            if (valid) {
+                if (lower) prev = base + (31 - __clz(lower));
+                else prev = S.head[h];
+            }
+            __syncwarp();
+            if (valid) {
+                S.delta[p] = (prev == 0xFFFFu) ? 0 : (uint16_t)(p - prev);
+                if ((grp >> lane) == 1u) S.head[h] = (uint16_t)p; /* newest of its group */
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    /* ---- per-position longest match: persistent lanes over a block-wide counter ---- */
+    {
+        const int W = prm.window, K = prm.chain_limit;
+        uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
+        bool active = false, exhausted = false;
+        int p = 0, qi = 0, dist = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
+        uint32_t w0 = 0, pb = 0;
+        for (;;) {
+            uint32_t idle = __ballot_sync(FULL, !active);
+            if (idle == FULL && exhausted) break;
+            if (!exhausted && (__popc(idle) >= REFILL_MIN_IDLE)) {
+                int cnt = __popc(idle), basep = 0;
+                if (lane == 0) basep = atomicAdd(&S.next_pos, cnt);
+                basep = __shfl_sync(FULL, basep, 0);
+                if (basep + cnt >= seglen) exhausted = true;
+                if (!active) {
+                    int i = basep + __popc(idle & lanemask_lt());
+                    if (i < seglen) {
+                        p = hist + i;
+                        maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;
+                        if (maxlen < DFL_MIN_MATCH) {
+                            out[i] = sd[soff + p];
+                        } else {
+                            active = true;
+                            qi = p; dist = 0; best_len = 2; best_dist = 0; hops = 0;
+                            w0 = ld4(S.data, soff + p) & 0xFFFFFFu;
+                        }
+                    }
+                }
+            }
+            if (active) {
+                bool done = false;
+                uint32_t d = S.delta[qi];
+                dist += d;
+                qi -= d;
+                if (d == 0 || dist > W || (K && hops >= K)) {
+                    done = true;
+                } else {
+                    hops++;
+                    bool cand;
+                    if (best_len == 2) cand = ((ld4(S.data, soff + qi) & 0xFFFFFFu) == w0);
+                    else cand = (sd[soff + qi + best_len] == pb);
+                    if (cand) {
+                        int len = 0;
+                        while (len < maxlen) {
+                            uint32_t x = ld4(S.data, soff + p + len) ^ ld4(S.data, soff + qi + len);
+                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                            len += 4;
+                        }
+                        if (len > maxlen) len = maxlen;
+                        if (len > best_len) {
+                            best_len = len;
+                            best_dist = dist;
+                            if (len == maxlen) done = true;
+                            else pb = sd[soff + p + len];
+                        }
+                    }
+                }
+                if (done) {
+                    out[p - hist] = best_len >= DFL_MIN_MATCH ? ((uint32_t)best_dist << 16) | (uint32_t)best_len
+                                                              : (uint32_t)sd[soff + p];
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_parse                                                                   */
+/* ------------------------------------------------------------------------- */
+
+#define PARSE_WARPS 8
+
+/*
+ * One warp per segment: the greedy token decision of process_loop
+ * (src/deflate_compress.c:265-288) -- from the segment start take the candidate
+ * at the current head, advance by its length (or 1 for a literal).  Tokens are
+ * compacted in place; lit/len and distance histograms (what aht_insert feeds,
+ * :270,:277-278, plus the one EOB of :234) are accumulated in shared memory.
+ */
+__global__ void __launch_bounds__(PARSE_WARPS * 32)
+k_parse(long long n, long long seg0, int nseg, dfl_params prm, uint32_t *__restrict__ tokcand, SegArrays A)
+{
+    __shared__ uint32_t s_hist[PARSE_WARPS][LLS + DS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = blockIdx.x * PARSE_WARPS + warp;
+    if (sl >= nseg) return;
+    const long long seg_lo = (seg0 + sl) * prm.seg_bytes;
+    const int seglen = (int)(((seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n) - seg_lo);
+    uint32_t *tc = tokcand + (size_t)sl * prm.seg_bytes;
+    uint32_t *hist = s_hist[warp];
+    for (int i = lane; i < LLS + DS; i += 32) hist[i] = 0;
+    __syncwarp();
+
+    int cur = 0, ntok = 0;
+    uint32_t extra = 0;
+    for (int base = 0; base < seglen; base += 32) {
+        int i = base + lane;
+        uint32_t v = i < seglen ? tc[i] : 0;
+        int adv = (v >> 16) ? (int)(v & 0xFFFF) : 1;
+        int lim = seglen - base < 32 ? seglen - base : 32;
+        uint32_t heads = 0;
+        int c = cur - base;
+        while (c < lim) {
+            heads |= 1u << c;
+            c += __shfl_sync(FULL, adv, c);
+        }
+        cur = base + c;
+        __syncwarp();
+        if ((heads >> lane) & 1) {
+            tc[ntok + __popc(heads & lanemask_lt())] = v;
+            if ((v >> 16) == 0) {
+                atomicAdd(&hist[v & 0xFF], 1u);
+            } else {
+                int eb, ev;
+                atomicAdd(&hist[len_sym((int)(v & 0xFFFF), eb, ev)], 1u);
+                extra += eb;
+                atomicAdd(&hist[LLS + dist_sym((int)(v >> 16), eb, ev)], 1u);
+                extra += eb;
+            }
+        }
+        ntok += __popc(heads);
+    }
+    for (int o = 16; o; o >>= 1) extra += __shfl_xor_sync(FULL, extra, o);
+    __syncwarp();
+    if (lane == 0) {
+        hist[256] += 1; /* end of block */
+        A.ntok[sl] = ntok;
+        A.extra[sl] = extra;
+    }
+    __syncwarp();
+    for (int i = lane; i < LLS; i += 32) A.ll_freq[(size_t)sl * LLS + i] = hist[i];
+    A.d_freq[(size_t)sl * DS + lane] = hist[LLS + lane];
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_huff                                                                    */
+/* ------------------------------------------------------------------------- */
+
+#define HUFF_WARPS 4
+
+struct HuffScratch {
+    uint32_t w[LLS];       /* padded weights, later internal node weights */
+    uint32_t sw[LLS];      /* sorted weights */
+    uint16_t ssym[LLS];    /* sorted symbols */
+    uint16_t lpar[LLS], ipar[LLS], idepth[LLS];
+    uint32_t iw[LLS];
+};
+
+struct HuffSmem {
+    uint32_t ll_freq[LLS], d_freq[DS], cl_freq[32];
+    uint8_t ll_len[LLS], d_len[DS], cl_len[32];
+    uint16_t ll_code[LLS], d_code[DS], cl_code[32];
+    uint8_t seq[LLS + DS + 8];
+    uint8_t item_sym[LLS + DS + 8], item_extra[LLS + DS + 8];
+    uint32_t hdr[HDR_WORDS];
+    HuffScratch sc;
+};
+
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+/*
+ * Length-limited Huffman code lengths, executed by one warp.  Bit-exact twin of
+ * orc_huff_lengths (oracle/deflate_oracle.c): used symbols padded to two, sort by
+ * (weight, symbol), two-queue merge with ties to the leaf queue (the
+ * construction of h_tree_builder_build, src/h_tree.c:242-280), leaf count per
+ * depth clipped at `limit` with Kraft repair, lengths handed out along the
+ * sorted order.
+ */
+__device__ void huff_lengths_warp(const uint32_t *freq, int n, int limit, uint8_t *len, HuffScratch &sc, int lane)
+{
+    int m = 0;
+    for (int s = lane; s < n; s += 32) {
+        uint32_t f = freq[s];
+        sc.w[s] = f;
+        len[s] = 0;
+        m += f != 0;
+    }
+    for (int o = 16; o; o >>= 1) m += __shfl_xor_sync(FULL, m, o);
+    __syncwarp();
+    if (m < 2) {
+        if (lane == 0) {
+            for (int s = 0; m < 2 && s < n; s++)
+                if (!sc.w[s]) { sc.w[s] = 1; m++; }
+        }
+        m = 2;
+        __syncwarp();
+    }
+    /* rank sort by key = weight << 9 | symbol (keys are distinct) */
+    for (int s = lane; s < n; s += 32) {
+        uint32_t ws = sc.w[s];
+        if (!ws) continue;
+        unsigned long long key = ((unsigned long long)ws << 9) | (uint32_t)s;
+        int r = 0;
+        for (int j = 0; j < n; j++) {
+            uint32_t wj = sc.w[j];
+            r += (wj != 0) && ((((unsigned long long)wj << 9) | (uint32_t)j) < key);
+        }
+        sc.sw[r] = ws;
+        sc.ssym[r] = (uint16_t)s;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int li = 0, ih = 0, it = 0;
+        while (it < m - 1) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (li < m && (ih >= it || sc.sw[li] <= sc.iw[ih])) { sum += sc.sw[li]; sc.lpar[li] = (uint16_t)it; li++; }
+                else { sum += sc.iw[ih]; sc.ipar[ih] = (uint16_t)it; ih++; }
+            }
+            sc.iw[it++] = sum;
+        }
+        sc.idepth[m - 2] = 0;
+        for (int i = m - 3; i >= 0; i--) sc.idepth[i] = sc.idepth[sc.ipar[i]] + 1;
+        int bl[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) bl[i] = 0;
+        int overflow = 0;
+        for (int i = 0; i < m; i++) {
+            int d = sc.idepth[sc.lpar[i]] + 1;
+            if (d > limit) { d = limit; overflow++; }
+            bl[d]++;
+        }
+        while (overflow > 0) {
+            int bits = limit - 1;
+            while (bl[bits] == 0) bits--;
+            bl[bits]--;
+            bl[bits + 1] += 2;
+            bl[limit]--;
+            overflow -= 2;
+        }
+        int j = 0;
+        for (int bits = limit; bits >= 1; bits--)
+            for (int i = 0; i < bl[bits]; i++) len[sc.ssym[j++]] = (uint8_t)bits;
+    }
+    __syncwarp();
+}
+
+/* Canonical codes (RFC 1951 3.2.2), bit-reversed for the LSB-first packer; lane 0. */
+__device__ void canonical_codes_lane0(const uint8_t *len, int n, uint16_t *code)
+{
+    int bl[16], next[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) bl[i] = 0;
+    for (int s = 0; s < n; s++) bl[len[s]]++;
+    bl[0] = 0;
+    int c = 0;
+    for (int b = 1; b <= 15; b++) {
+        c = (c + bl[b - 1]) << 1;
+        next[b] = c;
+    }
+    for (int s = 0; s < n; s++) {
+        int l = len[s];
+        code[s] = l ? (uint16_t)(__brev((uint32_t)next[l]++) >> (32 - l)) : 0;
+    }
+}
+
+struct BitW {
+    uint32_t *w;
+    uint32_t nbits;
+    __device__ void put(uint32_t v, int n)
+    {
+        uint32_t i = nbits >> 5, sh = nbits & 31;
+        w[i] |= v << sh;
+        if (sh + n > 32) w[i + 1] |= v >> (32 - sh);
+        nbits += n;
+    }
+};
+
+/*
+ * One warp per segment: code construction + exact block costs + choice.
+ * Twin of orc_emit_segment's front half (oracle/deflate_oracle.c); what the
+ * reference accounts per token in h_tree_d_lens / h_tree_builder_*
+ * (src/h_tree.c:75-148, :242-302) is done once per block here.
+ */
+__global__ void __launch_bounds__(HUFF_WARPS * 32)
+k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
+{
+    __shared__ HuffSmem s_all[HUFF_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = blockIdx.x * HUFF_WARPS + warp;
+    if (sl >= nseg) return;
+    HuffSmem &S = s_all[warp];
+    const long long seg_lo = (seg0 + sl) * prm.seg_bytes;
+    const long long seglen = ((seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n) - seg_lo;
+
+    for (int i = lane; i < LLS; i += 32) S.ll_freq[i] = i < NLL ? A.ll_freq[(size_t)sl * LLS + i] : 0;
+    S.d_freq[lane] = lane < ND ? A.d_freq[(size_t)sl * DS + lane] : 0;
+    S.cl_freq[lane] = 0;
+    for (int i = lane; i < HDR_WORDS; i += 32) S.hdr[i] = 0;
+    __syncwarp();
+
+    huff_lengths_warp(S.ll_freq, NLL, 15, S.ll_len, S.sc, lane);
+    huff_lengths_warp(S.d_freq, ND, 15, S.d_len, S.sc, lane);
+
+    int hlit = 0, hdist = 0, hclen = 0, nitems = 0;
+    if (lane == 0) {
+        for (hlit = NLL; hlit > 257 && S.ll_len[hlit - 1] == 0; hlit--) {}
+        for (hdist = ND; hdist > 1 && S.d_len[hdist - 1] == 0; hdist--) {}
+        int nseq = hlit + hdist;
+        for (int i = 0; i < hlit; i++) S.seq[i] = S.ll_len[i];
+        for (int i = 0; i < hdist; i++) S.seq[hlit + i] = S.d_len[i];
+        /* RFC 1951 3.2.7 run-length coding (what h_tree_d_lens counts, src/h_tree.c:87-136) */
+        int i = 0, k = 0;
+        while (i < nseq) {
+            int v = S.seq[i], j = i + 1;
+            while (j < nseq && S.seq[j] == v) j++;
+            int run = j - i;
+            if (v == 0) {
+                while (run >= 11) {
+                    int r = run < 138 ? run : 138;
+                    S.item_sym[k] = 18; S.item_extra[k] = (uint8_t)(r - 11); k++;
+                    run -= r;
+                }
+                if (run >= 3) { S.item_sym[k] = 17; S.item_extra[k] = (uint8_t)(run - 3); k++; run = 0; }
+                while (run-- > 0) { S.item_sym[k] = 0; S.item_extra[k] = 0; k++; }
+            } else {
+                S.item_sym[k] = (uint8_t)v; S.item_extra[k] = 0; k++;
+                run--;
+                while (run >= 3) {
+                    int r = run < 6 ? run : 6;
+                    S.item_sym[k] = 16; S.item_extra[k] = (uint8_t)(r - 3); k++;
+                    run -= r;
+                }
+                while (run-- > 0) { S.item_sym[k] = (uint8_t)v; S.item_extra[k] = 0; k++; }
+            }
+            i = j;
+        }
+        nitems = k;
+        for (i = 0; i < nitems; i++) S.cl_freq[S.item_sym[i]]++;
+    }
+    __syncwarp();
+    huff_lengths_warp(S.cl_freq, NCL, 7, S.cl_len, S.sc, lane);
+
+    /* exact costs */
+    unsigned long long dyn = 0, fix = 0;
+    for (int s = lane; s < NLL; s += 32) {
+        dyn += (unsigned long long)S.ll_freq[s] * S.ll_len[s];
+        fix += (unsigned long long)S.ll_freq[s] * fixed_ll_len(s);
+    }
+    if (lane < ND) {
+        dyn += (unsigned long long)S.d_freq[lane] * S.d_len[lane];
+        fix += (unsigned long long)S.d_freq[lane] * 5;
+    }
+    if (lane < NCL) {
+        dyn += (unsigned long long)S.cl_freq[lane] * S.cl_len[lane];
+        if (lane == 16) dyn += 2ull * S.cl_freq[16];
+        if (lane == 17) dyn += 3ull * S.cl_freq[17];
+        if (lane == 18) dyn += 7ull * S.cl_freq[18];
+    }
+    for (int o = 16; o; o >>= 1) {
+        dyn += __shfl_xor_sync(FULL, dyn, o);
+        fix += __shfl_xor_sync(FULL, fix, o);
+    }
+    int btype = 0;
+    unsigned long long block_bits = 0;
+    if (lane == 0) {
+        for (hclen = 19; hclen > 4 && S.cl_len[c_cl_order[hclen - 1]] == 0; hclen--) {}
+        unsigned long long extra = A.extra[sl];
+        dyn += 3 + 5 + 5 + 4 + 3 * hclen + extra;
+        fix += 3 + extra;
+        unsigned long long nstored = (unsigned long long)((seglen + 65534) / 65535);
+        if (nstored < 1) nstored = 1;
+        unsigned long long stored = 8ull * ((unsigned long long)seglen + 5 * nstored);
+        if (prm.block_mode == 1) btype = 0;
+        else if (prm.block_mode == 2) btype = 1;
+        else if (prm.block_mode == 3) btype = 2;
+        else if (stored <= fix && stored <= dyn) btype = 0;
+        else if (fix <= dyn) btype = 1;
+        else btype = 2;
+        block_bits = btype == 0 ? stored : btype == 1 ? fix : dyn;
+
+        BitW bw{S.hdr, 0};
+        if (btype == 2) {
+            canonical_codes_lane0(S.ll_len, NLL, S.ll_code);
+            canonical_codes_lane0(S.d_len, ND, S.d_code);
+            canonical_codes_lane0(S.cl_len, NCL, S.cl_code);
+            bw.put(0, 1);
+            bw.put(2, 2);
+            bw.put(hlit - 257, 5);
+            bw.put(hdist - 1, 5);
+            bw.put(hclen - 4, 4);
+            for (int i = 0; i < hclen; i++) bw.put(S.cl_len[c_cl_order[i]], 3);
+            for (int i = 0; i < nitems; i++) {
+                int cs = S.item_sym[i];
+                bw.put(S.cl_code[cs], S.cl_len[cs]);
+                if (cs == 16) bw.put(S.item_extra[i], 2);
+                else if (cs == 17) bw.put(S.item_extra[i], 3);
+                else if (cs == 18) bw.put(S.item_extra[i], 7);
+            }
+        } else if (btype == 1) {
+            bw.put(0, 1);
+            bw.put(1, 2);
+        }
+        A.hdr_bits[sl] = bw.nbits;
+        A.btype[sl] = btype;
+        A.block_bits[sl] = block_bits;
+        A.out_bytes[sl] = btype == 0 ? (uint32_t)(seglen + 5 * nstored + 5)
+                                     : (uint32_t)((block_bits + 3 + 7) / 8 + 4);
+    }
+    btype = __shfl_sync(FULL, btype, 0);
+    __syncwarp();
+    if (btype == 2) {
+        for (int s = lane; s < LLS; s += 32)
+            A.lltab[(size_t)sl * LLS + s] = s < NLL ? (uint32_t)S.ll_code[s] | ((uint32_t)S.ll_len[s] << 16) : 0;
+        A.dtab[(size_t)sl * DS + lane] = lane < ND ? (uint32_t)S.d_code[lane] | ((uint32_t)S.d_len[lane] << 16) : 0;
+        for (int i = lane; i < HDR_WORDS; i += 32) A.hdr[(size_t)sl * HDR_WORDS + i] = S.hdr[i];
+    } else if (btype == 1) {
+        /* fixed code of RFC 1951 3.2.6 */
+        for (int s = lane; s < LLS; s += 32) {
+            int l = fixed_ll_len(s);
+            uint32_t code = s < 144 ? 0x30 + s : s < 256 ? 0x190 + (s - 144) : s < 280 ? (s - 256) : 0xC0 + (s - 280);
+            A.lltab[(size_t)sl * LLS + s] = (__brev(code) >> (32 - l)) | ((uint32_t)l << 16);
+        }
+        A.dtab[(size_t)sl * DS + lane] = (__brev((uint32_t)lane) >> 27) | (5u << 16);
+        if (lane == 0) A.hdr[(size_t)sl * HDR_WORDS] = S.hdr[0];
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_scan                                                                    */
+/* ------------------------------------------------------------------------- */
+
+#define SCAN_THREADS 1024
+
+/* Exclusive scan of the segment sizes of one chunk -> byte offsets in the body. */
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan(int nseg, SegArrays A, DevState *state)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = state->total_out;
+    __syncthreads();
+    for (int base = 0; base < nseg; base += SCAN_THREADS) {
+        int i = base + tid;
+        unsigned long long v = i < nseg ? A.out_bytes[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long t = s_warp[lane], u = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(FULL, u, o);
+                if (lane >= o) u += y;
+            }
+            s_warp[lane] = u - t;
+        }
+        __syncthreads();
+        unsigned long long excl = s_carry + s_warp[warp] + x - v;
+        if (i < nseg) A.out_off[i] = excl;
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) state->total_out = s_carry;
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_emit                                                                    */
+/* ------------------------------------------------------------------------- */
+
+#define EMIT_THREADS 256
+#define EMIT_TPT 4
+#define EMIT_ROUND (EMIT_THREADS * EMIT_TPT)
+#define STG_WORDS 2048 /* 8 KB: 16 B shift + 640 B header + 1024 tokens * 48 bits + EOB/sync */
+
+__device__ __forceinline__ void stg_put(uint32_t *stg, uint32_t bitpos, unsigned long long v, int nb)
+{
+    if (nb == 0) return;
+    uint32_t i = bitpos >> 5, sh = bitpos & 31;
+    unsigned long long lo = v << sh;
+    atomicOr(&stg[i], (uint32_t)lo);
+    if (sh + nb > 32) atomicOr(&stg[i + 1], (uint32_t)(lo >> 32));
+    if (sh + nb > 64) atomicOr(&stg[i + 2], (uint32_t)(v >> (64 - sh)));
+}
+
+/*
+ * One CTA per segment: the bit packer the reference never wrote
+ * (src/deflate_compress.c:269,:279 "TODO: write lit / len/dist pair").
+ * Per round of 1024 tokens: each thread maps 4 tokens to (bits, nbits), a block
+ * exclusive scan gives every token its bit offset, codes are OR-ed into a shared
+ * staging buffer whose origin is congruent (mod 16 B) with the output address,
+ * and whole 16-byte words are stored to HBM.
+ */
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_emit(const uint8_t *__restrict__ d_in, long long n, long long seg0, long long last_seg, int is_final,
+       dfl_params prm, const uint32_t *__restrict__ tokcand, SegArrays A, uint8_t *__restrict__ d_out,
+       unsigned long long out_cap, DevState *state)
+{
+    __shared__ __align__(16) uint32_t stg[STG_WORDS];
+    __shared__ uint32_t s_ll[LLS], s_d[DS];
+    __shared__ uint32_t s_wsum[EMIT_THREADS / 32];
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sl = blockIdx.x;
+    const long long seg = seg0 + sl;
+    const long long seg_lo = seg * prm.seg_bytes;
+    const long long seglen = ((seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n) - seg_lo;
+    const unsigned long long off = A.out_off[sl];
+    const uint32_t out_bytes = A.out_bytes[sl];
+    const int btype = (int)A.btype[sl];
+    const uint32_t final_bit = (is_final && seg == last_seg) ? 1u : 0u;
+    if (off + out_bytes > out_cap) {
+        if (tid == 0) atomicExch(&state->error, 1u);
+        return;
+    }
+    uint8_t *dst = d_out + off;
+
+    if (btype == 0) {
+        /* stored block(s), RFC 1951 3.2.4, then the sync marker */
+        const uint8_t *src = d_in + seg_lo;
+        long long nst = (seglen + 65534) / 65535;
+        if (nst < 1) nst = 1;
+        for (long long b = 0; b < nst; b++) {
+            long long o = b * 65535, len = seglen - o < 65535 ? seglen - o : 65535;
+            uint8_t *q = dst + o + 5 * b;
+            if (tid == 0) {
+                q[0] = 0;
+                q[1] = (uint8_t)len; q[2] = (uint8_t)(len >> 8);
+                q[3] = (uint8_t)~len; q[4] = (uint8_t)(~len >> 8);
+            }
+            for (long long i = tid; i < len; i += EMIT_THREADS) q[5 + i] = src[o + i];
+        }
+        if (tid == 0) {
+            uint8_t *q = dst + seglen + 5 * nst;
+            q[0] = (uint8_t)final_bit; q[1] = 0; q[2] = 0; q[3] = 0xFF; q[4] = 0xFF;
+        }
+        return;
+    }
+
+    for (int i = tid; i < LLS; i += EMIT_THREADS) s_ll[i] = A.lltab[(size_t)sl * LLS + i];
+    if (tid < DS) s_d[tid] = A.dtab[(size_t)sl * DS + tid];
+    const uint32_t *tc = tokcand + (size_t)sl * prm.seg_bytes;
+    const int ntok = (int)A.ntok[sl];
+    const uint32_t hdr_bits = A.hdr_bits[sl];
+    const uint32_t *hdr = A.hdr + (size_t)sl * HDR_WORDS;
+
+    unsigned long long gpos = 0; /* bytes of this segment already stored */
+    uint32_t carry_n = 0, carry_v = 0;
+    const int nround = ntok == 0 ? 1 : (ntok + EMIT_ROUND - 1) / EMIT_ROUND;
+    for (int r = 0; r < nround; r++) {
+        const uint32_t sh = (uint32_t)((uintptr_t)(dst + gpos) & 15);
+        for (int i = tid; i < STG_WORDS; i += EMIT_THREADS) stg[i] = 0;
+        __syncthreads();
+        uint32_t bit0 = sh * 8 + carry_n;
+        if (tid == 0 && carry_n) atomicOr(&stg[sh >> 2], carry_v << ((sh & 3) * 8));
+        if (r == 0) {
+            for (uint32_t i = tid; i * 32 < hdr_bits; i += EMIT_THREADS) {
+                uint32_t nb = hdr_bits - i * 32 < 32 ? hdr_bits - i * 32 : 32;
+                stg_put(stg, bit0 + i * 32, hdr[i], (int)nb);
+            }
+            bit0 += hdr_bits;
+        }
+        /* map this thread's tokens */
+        unsigned long long cb[EMIT_TPT];
+        int cn[EMIT_TPT];
+        uint32_t tsum = 0;
+        const int t0 = r * EMIT_ROUND + tid * EMIT_TPT;
+#pragma unroll
+        for (int j = 0; j < EMIT_TPT; j++) {
+            cb[j] = 0; cn[j] = 0;
+            if (t0 + j < ntok) {
+                uint32_t t = tc[t0 + j];
+                if ((t >> 16) == 0) {
+                    uint32_t e = s_ll[t & 0xFF];
+                    cb[j] = e & 0xFFFF; cn[j] = e >> 16;
+                } else {
+                    int eb, ev;
+                    uint32_t e = s_ll[len_sym((int)(t & 0xFFFF), eb, ev)];
+                    unsigned long long bits = e & 0xFFFF;
+                    int nb = e >> 16;
+                    bits |= (unsigned long long)ev << nb; nb += eb;
+                    e = s_d[dist_sym((int)(t >> 16), eb, ev)];
+                    bits |= (unsigned long long)(e & 0xFFFF) << nb; nb += e >> 16;
+                    bits |= (unsigned long long)ev << nb; nb += eb;
+                    cb[j] = bits; cn[j] = nb;
+                }
+                tsum += cn[j];
+            }
+        }
+        /* block exclusive scan of tsum */
+        uint32_t x = tsum;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_wsum[warp] = x;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int w = 0; w < EMIT_THREADS / 32; w++) { uint32_t t = s_wsum[w]; s_wsum[w] = acc; acc += t; }
+            s_total = acc;
+        }
+        __syncthreads();
+        uint32_t bp = bit0 + s_wsum[warp] + x - tsum;
+#pragma unroll
+        for (int j = 0; j < EMIT_TPT; j++) {
+            stg_put(stg, bp, cb[j], cn[j]);
+            bp += cn[j];
+        }
+        uint32_t endbit = bit0 + s_total;
+        const bool last = (r == nround - 1);
+        if (last && tid == 0) {
+            /* end of block, then the empty stored block that byte-aligns the segment */
+            uint32_t e = s_ll[256];
+            stg_put(stg, endbit, e & 0xFFFF, (int)(e >> 16));
+            uint32_t eb2 = endbit + (e >> 16);
+            stg_put(stg, eb2, final_bit, 3);
+            uint32_t bytepos = (eb2 + 3 + 7) >> 3;
+            /* LEN = 0x0000, NLEN = 0xFFFF */
+            stg_put(stg, bytepos * 8 + 16, 0xFFFF, 16);
+        }
+        if (last) {
+            uint32_t e = s_ll[256];
+            endbit = (((endbit + (e >> 16) + 3 + 7) >> 3) + 4) * 8;
+        }
+        __syncthreads();
+        /* flush whole bytes [sh, e) */
+        const uint32_t e_byte = endbit >> 3;
+        const uint8_t *sb = reinterpret_cast<const uint8_t *>(stg);
+        uint8_t *gbase = dst + gpos - sh; /* 16 B aligned */
+        {
+            const uint32_t a0 = (sh + 15) & ~15u; /* first 16 B boundary >= sh */
+            const uint32_t a1 = e_byte & ~15u;    /* last 16 B boundary <= e */
+            if (a1 < a0) {
+                for (uint32_t i = sh + tid; i < e_byte; i += EMIT_THREADS) gbase[i] = sb[i];
+            } else {
+                for (uint32_t i = sh + tid; i < a0; i += EMIT_THREADS) gbase[i] = sb[i];
+                for (uint32_t i = a0 / 16 + tid; i < a1 / 16; i += EMIT_THREADS)
+                    reinterpret_cast<uint4 *>(gbase)[i] = reinterpret_cast<const uint4 *>(stg)[i];
+                for (uint32_t i = a1 + tid; i < e_byte; i += EMIT_THREADS) gbase[i] = sb[i];
+            }
+        }
+        carry_n = endbit & 7;
+        carry_v = carry_n ? (sb[e_byte] & ((1u << carry_n) - 1)) : 0;
+        gpos += e_byte - sh;
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_final + synth                                                           */
+/* ------------------------------------------------------------------------- */
+
+__global__ void k_final(long long n, DevState *state)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long s1 = (1 + state->adl_a) % ADLER_MOD;
+        unsigned long long s2 = ((unsigned long long)n % ADLER_MOD + state->adl_b) % ADLER_MOD;
+        state->adler = (unsigned int)((s2 << 16) | s1);
+    }
+}
+
+__device__ __host__ __forceinline__ unsigned long long splitmix64_at(unsigned long long seed, unsigned long long i)
+{
+    unsigned long long z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_synth_random(uint8_t *out, unsigned long long n, unsigned long long seed)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i * 8 < n; i += stride) {
+        unsigned long long z = splitmix64_at(seed, i);
+        if (i * 8 + 8 <= n && (((uintptr_t)out & 7) == 0)) {
+            reinterpret_cast<unsigned long long *>(out)[i] = z;
+        } else {
+            for (int k = 0; k < 8 && i * 8 + k < n; k++) out[i * 8 + k] = (uint8_t)(z >> (8 * k));
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* host side: context + C-ABI                                                */
+/* ------------------------------------------------------------------------- */
+
+struct dfl_ctx {
+    int device;
+    dfl_params prm;
+    /* chunk workspace */
+    size_t ws_segs, ws_seg_bytes;
+    uint32_t *tokcand;
+    SegArrays A;
+    void *seg_blob;
+    DevState *state;
+    DevState *h_state; /* pinned */
+    /* host-buffer path */
+    uint8_t *d_in, *d_out;
+    size_t d_in_cap, d_out_cap;
+    /* bookkeeping */
+    long launches;
+    long long last_n;
+    int pending;
+    /* token keeping */
+    int keep;
+    uint32_t *h_tokens;
+    size_t h_tokens_cap;
+    long nseg_kept;
+    uint32_t *h_ntok, *h_btype, *h_out_bytes;
+    unsigned long long *h_block_bits, *h_out_off;
+    size_t h_seg_cap;
+    /* timing */
+    int timing;
+    cudaEvent_t *ev;
+    int *ev_class;
+    int ev_n, ev_cap;
+    double k_ms[K_NUM];
+    char errbuf[256];
+};
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            if (ctx) snprintf(ctx->errbuf, sizeof(ctx->errbuf), "%s: %s", #call, cudaGetErrorString(e_)); \
+            return DFL_E_CUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+extern "C" void dfl_b200_default_params(dfl_params *p)
+{
+    p->window = DFL_MAX_WINDOW;
+    p->seg_bytes = DFL_MAX_SEG;
+    p->chain_limit = 0;
+    p->use_dict = 1;
+    p->block_mode = 0;
+}
+
+extern "C" const char *dfl_b200_strerror(int err)
+{
+    switch (err) {
+    case DFL_OK: return "ok";
+    case DFL_E_MALLOC: return "E_MALLOC: allocation failed";
+    case DFL_E_SZ: return "E_SZ: output buffer too small";
+    case DFL_E_RANGE: return "E_RANGE: parameter out of range";
+    case DFL_E_INVAL: return "E_INVAL: invalid argument";
+    case DFL_E_CUDA: return "CUDA failure (no sm_100 device, driver error or kernel fault)";
+    default: return "unknown error";
+    }
+}
+
+static int check_params(const dfl_params *p)
+{
+    if (p->window < 1 || p->window > DFL_MAX_WINDOW) return DFL_E_RANGE;
+    if (p->seg_bytes < 1 || p->seg_bytes > DFL_MAX_SEG) return DFL_E_RANGE;
+    if (p->chain_limit < 0) return DFL_E_RANGE;
+    if (p->block_mode < 0 || p->block_mode > 3) return DFL_E_RANGE;
+    return DFL_OK;
+}
+
+extern "C" size_t dfl_b200_bound(const dfl_params *prm, size_t n)
+{
+    size_t nseg = n ? (n + prm->seg_bytes - 1) / prm->seg_bytes : 0;
+    size_t b = n + nseg * (5 * ((prm->seg_bytes + 65534) / 65535) + 5 + 8) + 64;
+    /* a forced fixed/dynamic block may expand: <= 15 bits per literal + header */
+    if (prm->block_mode >= 2) b = 2 * n + nseg * 640 + 64;
+    return b;
+}
+
+static void free_ws(dfl_ctx *ctx)
+{
+    if (ctx->tokcand) cudaFree(ctx->tokcand);
+    if (ctx->seg_blob) cudaFree(ctx->seg_blob);
+    ctx->tokcand = NULL;
+    ctx->seg_blob = NULL;
+    ctx->ws_segs = 0;
+}
+
+static int ensure_ws(dfl_ctx *ctx, size_t nseg_chunk)
+{
+    if (ctx->ws_segs >= nseg_chunk && ctx->ws_seg_bytes == (size_t)ctx->prm.seg_bytes) return DFL_OK;
+    free_ws(ctx);
+    size_t ns = nseg_chunk;
+    CK(cudaMalloc(&ctx->tokcand, ns * ctx->prm.seg_bytes * sizeof(uint32_t)));
+    size_t per = (LLS + DS + LLS + DS + HDR_WORDS + 6) * sizeof(uint32_t) + 2 * sizeof(unsigned long long);
+    CK(cudaMalloc(&ctx->seg_blob, ns * per + 256));
+    unsigned char *p = (unsigned char *)ctx->seg_blob;
+    SegArrays &A = ctx->A;
+    A.block_bits = (unsigned long long *)p; p += ns * 8;
+    A.out_off = (unsigned long long *)p; p += ns * 8;
+    A.ll_freq = (uint32_t *)p; p += ns * LLS * 4;
+    A.d_freq = (uint32_t *)p; p += ns * DS * 4;
+    A.lltab = (uint32_t *)p; p += ns * LLS * 4;
+    A.dtab = (uint32_t *)p; p += ns * DS * 4;
+    A.hdr = (uint32_t *)p; p += ns * HDR_WORDS * 4;
+    A.ntok = (uint32_t *)p; p += ns * 4;
+    A.extra = (uint32_t *)p; p += ns * 4;
+    A.hdr_bits = (uint32_t *)p; p += ns * 4;
+    A.btype = (uint32_t *)p; p += ns * 4;
+    A.out_bytes = (uint32_t *)p; p += ns * 4;
+    ctx->ws_segs = ns;
+    ctx->ws_seg_bytes = ctx->prm.seg_bytes;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
+{
+    dfl_ctx *ctx = NULL;
+    int ndev = 0;
+    if (!out) return DFL_E_INVAL;
+    *out = NULL;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return DFL_E_CUDA; /* no CPU fallback */
+    if (device < 0 || device >= ndev) return DFL_E_RANGE;
+    ctx = (dfl_ctx *)calloc(1, sizeof(dfl_ctx));
+    if (!ctx) return DFL_E_MALLOC;
+    ctx->device = device;
+    if (prm) ctx->prm = *prm; else dfl_b200_default_params(&ctx->prm);
+    int rc = check_params(&ctx->prm);
+    if (rc) { free(ctx); return rc; }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        prop.major < 10) {
+        free(ctx);
+        return DFL_E_CUDA;
+    }
+    if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
+        cudaMalloc(&ctx->state, sizeof(DevState)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_state, sizeof(DevState)) != cudaSuccess) {
+        free(ctx);
+        return DFL_E_CUDA;
+    }
+    *out = ctx;
+    return DFL_OK;
+}
+
+extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_ws(ctx);
+    if (ctx->state) cudaFree(ctx->state);
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
+    free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_block_bits); free(ctx->h_out_off);
+    for (int i = 0; i < ctx->ev_cap; i++) cudaEventDestroy(ctx->ev[i]);
+    free(ctx->ev); free(ctx->ev_class);
+    free(ctx);
+}
+
+extern "C" int dfl_b200_set_params(dfl_ctx *ctx, const dfl_params *prm)
+{
+    if (!ctx || !prm) return DFL_E_INVAL;
+    int rc = check_params(prm);
+    if (rc) return rc;
+    ctx->prm = *prm;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_keep_tokens(dfl_ctx *ctx, int enable)
+{
+    if (!ctx) return DFL_E_INVAL;
+    ctx->keep = enable != 0;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_enable_timing(dfl_ctx *ctx, int enable)
+{
+    if (!ctx) return DFL_E_INVAL;
+    ctx->timing = enable != 0;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_num_kernels(void) { return K_NUM; }
+extern "C" const char *dfl_b200_kernel_name(int k) { return (k >= 0 && k < K_NUM) ? k_names[k] : ""; }
+extern "C" double dfl_b200_kernel_ms(dfl_ctx *ctx, int k) { return (ctx && k >= 0 && k < K_NUM) ? ctx->k_ms[k] : 0.0; }
+extern "C" long dfl_b200_kernel_launches(dfl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int ev_mark(dfl_ctx *ctx, int cls, cudaStream_t st)
+{
+    /* records one event; events come in (start, stop) pairs per launch */
+    if (!ctx->timing) return DFL_OK;
+    if (ctx->ev_n == ctx->ev_cap) {
+        int ncap = ctx->ev_cap ? ctx->ev_cap * 2 : 256;
+        cudaEvent_t *ne = (cudaEvent_t *)realloc(ctx->ev, ncap * sizeof(cudaEvent_t));
+        int *nc = (int *)realloc(ctx->ev_class, ncap * sizeof(int));
+        if (!ne || !nc) return DFL_E_MALLOC;
+        ctx->ev = ne; ctx->ev_class = nc;
+        for (int i = ctx->ev_cap; i < ncap; i++) CK(cudaEventCreate(&ctx->ev[i]));
+        ctx->ev_cap = ncap;
+    }
+    ctx->ev_class[ctx->ev_n] = cls;
+    CK(cudaEventRecord(ctx->ev[ctx->ev_n], st));
+    ctx->ev_n++;
+    return DFL_OK;
+}
+
+#define LAUNCH(cls, kern, grid, block, smem, st, ...)                 \
+    do {                                                              \
+        int r_ = ev_mark(ctx, cls, st);                               \
+        if (r_) return r_;                                            \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);                 \
+        ctx->launches++;                                              \
+        r_ = ev_mark(ctx, cls, st);                                   \
+        if (r_) return r_;                                            \
+    } while (0)
+
+static int keep_reserve(dfl_ctx *ctx, size_t n, size_t nseg)
+{
+    if (ctx->h_tokens_cap < n) {
+        if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
+        ctx->h_tokens = NULL;
+        ctx->h_tokens_cap = 0;
+        CK(cudaMallocHost(&ctx->h_tokens, (n ? n : 1) * sizeof(uint32_t)));
+        ctx->h_tokens_cap = n;
+    }
+    if (ctx->h_seg_cap < nseg) {
+        free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_block_bits); free(ctx->h_out_off);
+        ctx->h_ntok = (uint32_t *)malloc(nseg * 4);
+        ctx->h_btype = (uint32_t *)malloc(nseg * 4);
+        ctx->h_out_bytes = (uint32_t *)malloc(nseg * 4);
+        ctx->h_block_bits = (unsigned long long *)malloc(nseg * 8);
+        ctx->h_out_off = (unsigned long long *)malloc(nseg * 8);
+        if (!ctx->h_ntok || !ctx->h_btype || !ctx->h_out_bytes || !ctx->h_block_bits || !ctx->h_out_off) return DFL_E_MALLOC;
+        ctx->h_seg_cap = nseg;
+    }
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len,
+                                        int is_final, uint8_t *d_out, size_t out_cap, void *stream)
+{
+    if (!ctx || (!d_in && n) || !d_out) return DFL_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    const dfl_params prm = ctx->prm;
+    const size_t nseg = n ? (n + prm.seg_bytes - 1) / prm.seg_bytes : 0;
+    size_t chunk_segs = DFL_CHUNK_BYTES / (size_t)prm.seg_bytes;
+    if (chunk_segs > nseg) chunk_segs = nseg;
+    if (chunk_segs < 1) chunk_segs = 1;
+    int rc = ensure_ws(ctx, chunk_segs);
+    if (rc) return rc;
+    ctx->ev_n = 0;
+    ctx->last_n = (long long)n;
+    ctx->nseg_kept = 0;
+    if (ctx->keep) {
+        rc = keep_reserve(ctx, n, nseg);
+        if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(ctx->state, 0, sizeof(DevState), st));
+    if (n == 0) {
+        /* empty input: a lone empty stored block */
+        static const uint8_t empty_final[5] = {1, 0, 0, 0xFF, 0xFF}, empty_more[5] = {0, 0, 0, 0xFF, 0xFF};
+        if (out_cap < 5) return DFL_E_SZ;
+        CK(cudaMemcpyAsync(d_out, is_final ? empty_final : empty_more, 5, cudaMemcpyHostToDevice, st));
+        unsigned long long five = 5;
+        CK(cudaMemcpyAsync(&ctx->state->total_out, &five, 8, cudaMemcpyHostToDevice, st));
+    }
+    for (size_t s0 = 0; s0 < nseg; s0 += chunk_segs) {
+        int ns = (int)(nseg - s0 < chunk_segs ? nseg - s0 : chunk_segs);
+        LAUNCH(K_MATCH, k_match, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
+               (long long)s0, prm, ctx->tokcand, ctx->state);
+        LAUNCH(K_PARSE, k_parse, (ns + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st, (long long)n,
+               (long long)s0, ns, prm, ctx->tokcand, ctx->A);
+        LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
+               (long long)s0, ns, prm, ctx->A);
+        LAUNCH(K_SCAN, k_scan, 1, SCAN_THREADS, 0, st, ns, ctx->A, ctx->state);
+        LAUNCH(K_EMIT, k_emit, ns, EMIT_THREADS, 0, st, d_in, (long long)n, (long long)s0, (long long)(nseg - 1),
+               is_final, prm, ctx->tokcand, ctx->A, d_out, (unsigned long long)out_cap, ctx->state);
+        if (ctx->keep) {
+            /* debug / fd_stats path: pull this chunk's tokens and segment records */
+            size_t pos0 = s0 * (size_t)prm.seg_bytes;
+            size_t cnt = (size_t)ns * prm.seg_bytes;
+            if (pos0 + cnt > n) cnt = n - pos0;
+            CK(cudaMemcpyAsync(ctx->h_tokens + pos0, ctx->tokcand, cnt * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_ntok + s0, ctx->A.ntok, ns * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_btype + s0, ctx->A.btype, ns * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_out_bytes + s0, ctx->A.out_bytes, ns * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_block_bits + s0, ctx->A.block_bits, ns * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_out_off + s0, ctx->A.out_off, ns * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ctx->nseg_kept = (long)(s0 + ns);
+        }
+    }
+    LAUNCH(K_FINAL, k_final, 1, 32, 0, st, (long long)n, ctx->state);
+    CK(cudaGetLastError());
+    ctx->pending = 1;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_deflate_finish(dfl_ctx *ctx, size_t *out_len, uint32_t *adler, void *stream)
+{
+    if (!ctx || !ctx->pending) return DFL_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(ctx->h_state, ctx->state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->pending = 0;
+    if (ctx->timing) {
+        for (int k = 0; k < K_NUM; k++) ctx->k_ms[k] = 0;
+        for (int i = 0; i + 1 < ctx->ev_n; i += 2) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+            ctx->k_ms[ctx->ev_class[i]] += ms;
+        }
+    }
+    if (ctx->h_state->error) return DFL_E_SZ;
+    if (out_len) *out_len = (size_t)ctx->h_state->total_out;
+    if (adler) *adler = ctx->h_state->adler;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_deflate_device(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len,
+                                       int is_final, uint8_t *d_out, size_t out_cap, size_t *out_len,
+                                       uint32_t *adler, void *stream)
+{
+    int rc = dfl_b200_deflate_enqueue(ctx, d_in, n, hist_len, is_final, d_out, out_cap, stream);
+    if (rc) return rc;
+    return dfl_b200_deflate_finish(ctx, out_len, adler, stream);
+}
+
+extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                      size_t *out_len)
+{
+    if (!ctx || (!in && n) || !out || !out_len) return DFL_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    size_t bound = dfl_b200_bound(&ctx->prm, n);
+    if (ctx->d_in_cap < n + 16) {
+        if (ctx->d_in) cudaFree(ctx->d_in);
+        ctx->d_in = NULL; ctx->d_in_cap = 0;
+        CK(cudaMalloc(&ctx->d_in, n + 16));
+        ctx->d_in_cap = n + 16;
+    }
+    if (ctx->d_out_cap < bound + 16) {
+        if (ctx->d_out) cudaFree(ctx->d_out);
+        ctx->d_out = NULL; ctx->d_out_cap = 0;
+        CK(cudaMalloc(&ctx->d_out, bound + 16));
+        ctx->d_out_cap = bound + 16;
+    }
+    cudaStream_t st = 0;
+    if (n) CK(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, st));
+    size_t body = 0;
+    uint32_t adler = 1;
+    /* body at d_out + 2 so the zlib header can be prepended without a second copy */
+    int rc = dfl_b200_deflate_device(ctx, ctx->d_in, n, 0, 1, ctx->d_out + 2, bound, &body, &adler, st);
+    if (rc) return rc;
+    if (cap < body + 6) return DFL_E_SZ;
+    CK(cudaMemcpyAsync(out + 2, ctx->d_out + 2, body, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out[0] = 0x78; /* CM = 8, CINFO = 7: header the decoder checks at src/deflate_decompress.c:352-360 */
+    out[1] = 0x9C;
+    out[2 + body + 0] = (uint8_t)(adler >> 24); /* RFC 1950: Adler-32 MSB first */
+    out[2 + body + 1] = (uint8_t)(adler >> 16);
+    out[2 + body + 2] = (uint8_t)(adler >> 8);
+    out[2 + body + 3] = (uint8_t)adler;
+    *out_len = body + 6;
+    return DFL_OK;
+}
+
+extern "C" long dfl_b200_num_segments(dfl_ctx *ctx) { return ctx ? ctx->nseg_kept : 0; }
+
+extern "C" int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info)
+{
+    if (!ctx || !info || seg < 0 || seg >= ctx->nseg_kept) return DFL_E_RANGE;
+    info->btype = (int32_t)ctx->h_btype[seg];
+    info->ntokens = (int32_t)ctx->h_ntok[seg];
+    info->block_bits = (int64_t)ctx->h_block_bits[seg];
+    info->out_bytes = (int64_t)ctx->h_out_bytes[seg];
+    info->out_offset = (int64_t)ctx->h_out_off[seg];
+    return DFL_OK;
+}
+
+extern "C" long dfl_b200_tokens(dfl_ctx *ctx, long seg, uint32_t *tokens, long cap)
+{
+    if (!ctx || seg < 0 || seg >= ctx->nseg_kept) return DFL_E_RANGE;
+    long nt = (long)ctx->h_ntok[seg];
+    if (tokens) {
+        if (cap < nt) return DFL_E_SZ;
+        memcpy(tokens, ctx->h_tokens + (size_t)seg * ctx->prm.seg_bytes, (size_t)nt * 4);
+    }
+    return nt;
+}
+
+extern "C" int dfl_b200_synth_random(uint8_t *d_out, size_t n, uint64_t seed, void *stream)
+{
+    dfl_ctx *ctx = NULL;
+    k_synth_random<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_out, (unsigned long long)n, (unsigned long long)seed);
+    CK(cudaGetLastError());
+    return DFL_OK;
+}

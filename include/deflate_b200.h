@@ -1,0 +1,130 @@
+/*
+ * include/deflate_b200.h -- thin C-ABI over the sm_100a DEFLATE kernels.
+ *
+ * This is the layer the reference-facing host code (include/deflate_ext.h,
+ * csrc/host/deflate_compress.c) calls; it is also what a cgo/JNI/ctypes binding
+ * would bind.  Plain pointers and sizes only.  There is NO CPU fallback: every
+ * entry point fails with DFL_E_CUDA when no sm_100 device / driver is present.
+ *
+ * What each entry point replaces in the reference (mparker97/deflate_compression):
+ *   dfl_b200_deflate_device / _compress_host
+ *       process_loop(), src/deflate_compress.c:219-347: hash-chain longest-match
+ *       search (:244-263, check_dup_str :164-180), greedy token decision
+ *       (:265-288), per-token code mapping (get_len_code/get_dist_code :182-217)
+ *       and the cost accounting it feeds (h_tree_d_lens / h_tree_builder_*,
+ *       src/h_tree.c:75-302) -- completed with the encode side the reference
+ *       leaves as TODOs (:269,:279): length-limited code lengths, canonical
+ *       codes, stored/fixed/dynamic choice (README.md:16,19), bit packing and
+ *       the zlib container the decoder demands (src/deflate_decompress.c:347-368,
+ *       :402-404).
+ *   dfl_b200_tokens
+ *       the per-token (ll, d) fields of struct compress_stats written to
+ *       fd_stats (src/include/deflate_ext.h:19-31, src/deflate_compress.c:291-309).
+ *   dfl_params.window
+ *       the `swi sw` argument of deflate_compress (src/include/deflate_ext.h:17).
+ */
+#ifndef DEFLATE_B200_H
+#define DEFLATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFL_MIN_MATCH 3       /* src/deflate_compress.c:247 */
+#define DFL_MAX_MATCH 258     /* src/include/deflate.h:4 */
+#define DFL_MAX_WINDOW 32768  /* README.md:6 */
+#define DFL_MAX_SEG 32768     /* one segment = one CTA-resident window pair */
+#define DFL_HASH_BITS 14      /* bucket hash width; observable only with chain_limit > 0 */
+/* bucket of the 3 bytes packed little-endian in v (low 24 bits) */
+#define DFL_HASH3(v) ((((uint32_t)(v) & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - DFL_HASH_BITS))
+
+/* error codes: 0 ok, negative on error (reference convention: callers test < 0,
+ * src/png/png_decoder.c:249).  Values reuse src/include/global_errors.h:24-35. */
+#define DFL_OK 0
+#define DFL_E_MALLOC (-2)   /* E_MALLOC */
+#define DFL_E_SZ (-6)       /* E_SZ: output buffer too small */
+#define DFL_E_RANGE (-10)   /* E_RANGE */
+#define DFL_E_INVAL (-11)   /* E_INVAL */
+#define DFL_E_CUDA (-100)   /* CUDA runtime / driver / device failure */
+
+typedef struct dfl_ctx dfl_ctx;
+
+typedef struct dfl_params {
+    int32_t window;      /* 1..32768; reference `sw` */
+    int32_t seg_bytes;   /* 1..32768; independent segment (parse restart, one block + sync marker) */
+    int32_t chain_limit; /* 0 = walk the whole chain (reference); K = newest K bucket entries */
+    int32_t use_dict;    /* 1 = segments may match into the preceding <= window bytes */
+    int32_t block_mode;  /* 0 = cheapest of stored/fixed/dynamic; 1/2/3 force stored/fixed/dynamic */
+} dfl_params;
+
+typedef struct dfl_seg_info {
+    int32_t btype;       /* 0 stored, 1 fixed, 2 dynamic */
+    int32_t ntokens;
+    int64_t block_bits;  /* chosen block incl. 3 header bits, excl. sync marker */
+    int64_t out_bytes;   /* bytes of this segment in the stream incl. sync marker */
+    int64_t out_offset;  /* byte offset of the segment in the deflate body */
+} dfl_seg_info;
+
+void dfl_b200_default_params(dfl_params *p);
+const char *dfl_b200_strerror(int err);
+
+/* Context bound to one CUDA device.  Workspace is allocated lazily and reused. */
+int dfl_b200_create(dfl_ctx **ctx, int device, const dfl_params *prm);
+void dfl_b200_destroy(dfl_ctx *ctx);
+int dfl_b200_set_params(dfl_ctx *ctx, const dfl_params *prm);
+
+/* Upper bound of the raw deflate body for n input bytes. */
+size_t dfl_b200_bound(const dfl_params *prm, size_t n);
+
+/*
+ * Device-resident compress: d_in[0,n) -> raw DEFLATE body at d_out.
+ * d_in[-hist_len, 0) must be readable device memory holding the bytes that
+ * precede this range in the stream (dictionary priming for a shard; 0 for a
+ * whole stream).  The last segment's sync marker carries BFINAL iff is_final.
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default) up to the final
+ * size read-back; *out_len and *adler (Adler-32 of d_in[0,n) from start value
+ * 1) are valid on return.
+ */
+int dfl_b200_deflate_device(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len,
+                            int is_final, uint8_t *d_out, size_t out_cap, size_t *out_len,
+                            uint32_t *adler, void *stream);
+
+/* Same, but enqueue only: sizes stay on the device until dfl_b200_deflate_finish(). */
+int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len,
+                             int is_final, uint8_t *d_out, size_t out_cap, void *stream);
+int dfl_b200_deflate_finish(dfl_ctx *ctx, size_t *out_len, uint32_t *adler, void *stream);
+
+/*
+ * Host-buffer compress (the call behind deflate_compress()): copies in[0,n) to
+ * the device, compresses, and copies a complete zlib (RFC 1950) stream back
+ * into out.  H2D and D2H are inside the call.
+ */
+int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                           size_t *out_len);
+
+/* Parity / fd_stats support: keep the token stream of the next compress calls
+ * on the host (4 bytes per input byte).  Token = literal byte, or dist<<16|len. */
+int dfl_b200_keep_tokens(dfl_ctx *ctx, int enable);
+long dfl_b200_num_segments(dfl_ctx *ctx);
+int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info);
+long dfl_b200_tokens(dfl_ctx *ctx, long seg, uint32_t *tokens, long cap);
+
+/* Number of kernels this context has launched (bench.py's gpu_launches). */
+long dfl_b200_kernel_launches(dfl_ctx *ctx);
+/* Device milliseconds of each kernel class over the last deflate call
+ * (CUDA events on the launch stream); names via dfl_b200_kernel_name(). */
+int dfl_b200_enable_timing(dfl_ctx *ctx, int enable);
+int dfl_b200_num_kernels(void);
+const char *dfl_b200_kernel_name(int k);
+double dfl_b200_kernel_ms(dfl_ctx *ctx, int k);
+
+/* Synthetic corpora generated on the device (bench/test support). */
+int dfl_b200_synth_random(uint8_t *d_out, size_t n, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

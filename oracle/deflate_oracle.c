@@ -545,6 +545,7 @@ long orc_bound(long n, const orc_params *prm)
 {
     long nseg = orc_num_segments(n, prm);
     long per = 5 * ((prm->seg_bytes + 65534) / 65535) + 5 + 8;
+    if (prm->block_mode >= 2) return 2 * n + nseg * 640 + 64; /* forced fixed/dynamic may expand */
     return n + nseg * per + 64;
 }
 

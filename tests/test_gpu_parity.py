@@ -1,0 +1,251 @@
+"""GPU parity tests (-m gpu): every call goes through the C-ABI of
+libdeflate_b200.so; the CPU oracle is only the checker.
+
+Bar: bit-exact.  (a) the per-segment token stream equals the oracle's and, for
+no-dictionary 32 KiB segments, the real reference's (golden fixtures made from
+oracle/_ref); (b) the emitted stream equals the oracle's byte for byte;
+(c) every stream inflates to the input through zlib, the oracle's repaired
+deflate_decompress and the product's deflate_decompress."""
+import hashlib
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases, make_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D(built):
+    return built
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import pyoracle
+
+    return pyoracle
+
+
+def gpu_tokens(comp):
+    return [comp.tokens(s).copy() for s in range(comp.num_segments())]
+
+
+def check_stream(D, O, data: np.ndarray, **prm):
+    """Compress on the GPU with token keeping; compare tokens + bytes with the oracle."""
+    comp = D.Compressor(**prm)
+    comp.keep_tokens(True)
+    z = comp.compress(data)
+    op = O.params(**prm)
+    zo = O.zlib_compress(data, op)
+    n = data.size
+    seg = prm.get("seg_bytes", 32768)
+    nseg = (n + seg - 1) // seg
+    assert comp.num_segments() == nseg
+    for s in range(nseg):
+        lo, hi = s * seg, min(n, (s + 1) * seg)
+        ot = O.lz77_segment(data, 0, lo, hi, op)
+        gt = comp.tokens(s)
+        assert gt.size == ot.size and np.array_equal(gt, ot), f"token mismatch in segment {s}"
+    assert z == zo, "stream differs from the oracle's"
+    raw = data.tobytes()
+    assert zlib.decompress(z) == raw
+    assert O.zlib_decompress(z, n) == raw
+    assert D.deflate_decompress(z) == raw
+    comp.close()
+    return z
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c[0])
+def test_golden_reference_tokens(D, O, case):
+    """Token stream of a no-dictionary segment == the real reference's (fixture)."""
+    name, kind, seed, off, n, ref_toks, last, sha = case
+    data = make_input(kind, seed, off, n)
+    assert hashlib.sha256(data.tobytes()).digest() == sha.tobytes()
+    comp = D.Compressor(use_dict=0)
+    comp.keep_tokens(True)
+    z = comp.compress(data)
+    assert comp.num_segments() == 1
+    gt = comp.tokens(0)
+    assert gt.size == ref_toks.size and np.array_equal(gt, ref_toks)
+    assert zlib.decompress(z) == data.tobytes()
+    comp.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 32, 33, 257, 258, 259, 260, 1000, 32767, 32768, 32769, 65535,
+                               65536, 65537, 100000])
+def test_sizes_text(D, O, n):
+    check_stream(D, O, make_input("markov", 1, 12345, n))
+
+
+def test_empty(D, O):
+    comp = D.Compressor()
+    z = comp.compress(b"")
+    assert z == O.zlib_compress(b"", O.params())
+    assert zlib.decompress(z) == b""
+
+
+@pytest.mark.parametrize("kind,seed", [("markov", 2), ("random", 4), ("log", 3), ("png", 6), ("zeros", 0),
+                                        ("period7", 0), ("const_a", 0)])
+def test_kinds_multi_segment(D, O, kind, seed):
+    check_stream(D, O, make_input(kind, seed, 0, 200000))
+
+
+@pytest.mark.parametrize("prm", [
+    dict(seg_bytes=4096), dict(seg_bytes=4096, use_dict=0), dict(seg_bytes=1000), dict(seg_bytes=32768, use_dict=0),
+    dict(window=1024), dict(window=4096, seg_bytes=8192), dict(window=1), dict(window=32767),
+    dict(chain_limit=1), dict(chain_limit=8), dict(chain_limit=128, seg_bytes=16384),
+    dict(block_mode=1), dict(block_mode=2), dict(block_mode=3),
+], ids=str)
+def test_params(D, O, prm):
+    for kind, seed in (("markov", 1), ("log", 3), ("random", 4)):
+        check_stream(D, O, make_input(kind, seed, 0, 150001), **prm)
+
+
+def test_mixed_blocks(D, O):
+    """Text, random and zero stripes: stored, dynamic (and possibly fixed) blocks in one stream."""
+    parts = [make_input("markov", 1, 0, 40000), make_input("random", 4, 0, 50000), make_input("zeros", 0, 0, 70000),
+             make_input("markov", 2, 0, 20), make_input("random", 9, 0, 40)]
+    data = np.concatenate(parts)
+    comp = D.Compressor()
+    comp.keep_tokens(True)
+    z = comp.compress(data)
+    types = {comp.seg_info(s).btype for s in range(comp.num_segments())}
+    assert 0 in types and 2 in types
+    assert z == O.zlib_compress(data, O.params())
+    assert zlib.decompress(z) == data.tobytes()
+
+
+def test_tiny_inputs_all_lengths(D, O):
+    base = make_input("markov", 1, 0, 64)
+    comp = D.Compressor()
+    for n in range(0, 40):
+        z = comp.compress(base[:n])
+        assert z == O.zlib_compress(base[:n], O.params())
+        assert zlib.decompress(z) == base[:n].tobytes()
+
+
+def test_deep_huffman_tree(D, O):
+    """Fibonacci-weighted literals force code lengths past 15: the length limiter must agree with the oracle."""
+    fib = [1, 1]
+    while len(fib) < 22:
+        fib.append(fib[-1] + fib[-2])
+    rng = np.random.default_rng(7)
+    sym = np.concatenate([np.full(f, i * 7 + 3, dtype=np.uint8) for i, f in enumerate(fib)])
+    rng.shuffle(sym)
+    data = sym[:32768]
+    check_stream(D, O, data, block_mode=3)
+
+
+def test_fd_api_roundtrip(D, O, tmp_path):
+    """The reference entry point: deflate_compress(fd_in, fd_out, fd_stats, sw, ops)."""
+    data = make_input("markov", 2, 0, 300000)
+    src, dst, st = tmp_path / "in", tmp_path / "out.z", tmp_path / "stats"
+    src.write_bytes(data.tobytes())
+    fi = os.open(src, os.O_RDONLY)
+    fo = os.open(dst, os.O_WRONLY | os.O_CREAT)
+    fs = os.open(st, os.O_WRONLY | os.O_CREAT)
+    try:
+        assert D.deflate_compress(fi, fo, fs, 32768, 0) == 0
+    finally:
+        os.close(fi), os.close(fo), os.close(fs)
+    z = dst.read_bytes()
+    assert z == O.zlib_compress(data, O.params())
+    assert D.deflate_decompress(z) == data.tobytes()
+    # fd_stats: expanding the (ll, d) records reproduces the input (tests/check_lld.c method)
+    recs = np.frombuffer(st.read_bytes(), dtype=np.int32).reshape(-1, 6)
+    toks = O.ref_records_to_tokens(recs)
+    assert recs[0, 0] == 1
+    out = bytearray()
+    for ll, d in zip(recs[:, 4], recs[:, 5]):
+        if d == 0:
+            out.append(int(ll) & 0xFF)
+        else:
+            for _ in range(int(ll)):
+                out.append(out[-int(d)])
+    assert bytes(out) == data.tobytes()
+    assert toks.size == recs.shape[0]
+
+
+def test_fd_api_pipe_and_errors(D):
+    r, w = os.pipe()
+    os.write(w, b"hello hello hello hello")
+    os.close(w)
+    r2, w2 = os.pipe()
+    assert D.deflate_compress(r, w2, -1, 32768, 0) == 0
+    os.close(w2)
+    z = os.read(r2, 1 << 16)
+    os.close(r), os.close(r2)
+    assert zlib.decompress(z) == b"hello hello hello hello"
+    r, w = os.pipe()
+    os.close(w)
+    assert D.deflate_compress(r, -1, -1, 0, 0) < 0  # window 0 is out of range
+    os.close(r)
+
+
+def test_device_api_shard_with_history(D, O):
+    """dfl_b200_deflate_device on a shard that is primed with the preceding bytes (multi-GPU building block)."""
+    import torch
+
+    data = make_input("markov", 5, 0, 400000)
+    cut = 3 * 32768 + 5000  # shard boundary (not a multiple of the segment size on purpose)
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(data).to(dev)
+    comp = D.Compressor()
+    bodies, adlers = [], []
+    for lo, hi, final in ((0, cut, False), (cut, data.size, True)):
+        n = hi - lo
+        hist = min(lo, 32768)
+        cap = comp.bound(n)
+        d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        out_len, adler = comp.deflate_device(d_in.data_ptr() + lo, n, hist, final, d_out.data_ptr(), cap)
+        body = d_out[:out_len].cpu().numpy().tobytes()
+        ob, _ = O.deflate_body(data, lo, hi, O.params(), is_final=final)
+        assert body == ob
+        assert adler == O.adler32(data[lo:hi])
+        bodies.append(body)
+        adlers.append((adler, n))
+    a = adlers[0][0]
+    a = O.adler32_combine(a, adlers[1][0], adlers[1][1])
+    stream = b"\x78\x9c" + b"".join(bodies) + a.to_bytes(4, "big")
+    assert zlib.decompress(stream) == data.tobytes()
+
+
+def test_large_roundtrip_properties(D, O):
+    """64 MiB of text: size-independent properties (round trip, segment accounting, Adler-32)."""
+    n = 64 << 20
+    data = make_input("markov", 2, 0, n)
+    comp = D.Compressor()
+    z = comp.compress(data)
+    raw = zlib.decompress(z)
+    assert len(raw) == n and raw == data.tobytes()
+    assert int.from_bytes(z[-4:], "big") == zlib.adler32(raw)
+    # first and last segments against the oracle
+    comp.keep_tokens(True)
+    z2 = comp.compress(data)
+    assert z2 == z
+    op = O.params()
+    for s in (0, 1, n // 32768 - 1):
+        assert np.array_equal(comp.tokens(s), O.lz77_segment(data, 0, s * 32768, (s + 1) * 32768, op))
+
+
+def test_unaligned_device_pointers(D, O):
+    import torch
+
+    data = make_input("log", 3, 0, 100000)
+    dev = torch.device("cuda:0")
+    comp = D.Compressor()
+    for shift_in, shift_out in ((1, 0), (3, 5), (7, 13), (15, 1)):
+        buf = torch.zeros(data.size + 64, dtype=torch.uint8, device=dev)
+        buf[shift_in:shift_in + data.size] = torch.from_numpy(data).to(dev)
+        cap = comp.bound(data.size)
+        d_out = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+        out_len, adler = comp.deflate_device(buf.data_ptr() + shift_in, data.size, 0, True,
+                                             d_out.data_ptr() + shift_out, cap)
+        body = d_out[shift_out:shift_out + out_len].cpu().numpy().tobytes()
+        ob, _ = O.deflate_body(data, 0, data.size, O.params(), is_final=True)
+        assert body == ob
+        assert int(d_out[shift_out + out_len:].max()) == 0 and int(d_out[:shift_out].sum()) == 0
