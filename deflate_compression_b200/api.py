@@ -58,8 +58,8 @@ def lib_path() -> str:
 
 def build(force: bool = False) -> None:
     """Compile libdeflate_b200.so + zencode in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
-    if force or not os.path.exists(_LIB):
-        subprocess.run(["make", "-C", os.path.join(PKG, "csrc"), "-s"], check=True)
+    del force  # make decides what is stale
+    subprocess.run(["make", "-C", os.path.join(PKG, "csrc"), "-s"], check=True)
 
 
 def lib() -> C.CDLL:
@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
         L.dfl_b200_kernel_name.argtypes = [C.c_int]
         L.dfl_b200_kernel_ms.restype = C.c_double
         L.dfl_b200_kernel_ms.argtypes = [vp, C.c_int]
+        L.dfl_b200_phase_cycles.restype = C.c_uint64
+        L.dfl_b200_phase_cycles.argtypes = [vp, C.c_int]
         L.dfl_b200_synth_random.argtypes = [vp, C.c_size_t, C.c_uint64, vp]
         # reference API (include/deflate_ext.h)
         L.deflate_compress.restype = C.c_int
@@ -215,6 +217,10 @@ class Compressor:
         L = lib()
         return {L.dfl_b200_kernel_name(k).decode(): float(L.dfl_b200_kernel_ms(self._ctx, k))
                 for k in range(L.dfl_b200_num_kernels())}
+
+    def phase_cycles(self) -> dict:
+        names = ("stage_in", "build", "search", "total")
+        return {nm: int(lib().dfl_b200_phase_cycles(self._ctx, k)) for k, nm in enumerate(names)}
 
     def kernel_launches(self) -> int:
         return int(lib().dfl_b200_kernel_launches(self._ctx))

@@ -39,7 +39,7 @@
 #define DS 32            /* stride of per-segment distance tables */
 #define HDR_WORDS 160    /* 640 B >= 3+14+57+316*14 bits */
 #define NPOS_MAX 65536
-#define HASH_SIZE (1 << DFL_HASH_BITS)
+#define HASH_SIZE DFL_HASH_BUCKETS
 #define MATCH_THREADS 1024
 #define REFILL_MIN_IDLE 8
 #define DFL_CHUNK_BYTES (256u << 20)
@@ -54,6 +54,7 @@ struct DevState {
     unsigned long long adl_b;      /* sum of per-segment weighted sums */
     unsigned int error;            /* 1 = output overflow */
     unsigned int adler;            /* final Adler-32 */
+    unsigned long long t_phase[4]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
 };
 
 struct SegArrays {
@@ -155,25 +156,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 /* k_match                                                                   */
 /* ------------------------------------------------------------------------- */
 
+#define MATCH_CHUNK 32   /* positions per speculative parse chunk */
+#define HOP_BATCH 8      /* chain hops a lane takes before the warp re-converges */
+#define BUILD_WARP (MATCH_THREADS / 32 - 1)
+
 struct MatchSmem {
     uint32_t data[(NPOS_MAX + 64) / 4]; /* [window | segment] bytes, 16 B of slack either side */
     uint16_t delta[NPOS_MAX];           /* distance to the previous position of the same bucket, 0 = none */
     uint16_t head[HASH_SIZE];           /* newest position of each bucket, 0xFFFF = empty */
+    uint32_t claimed[DFL_MAX_SEG / 32]; /* segment positions some lane has taken as a parse head */
     uint64_t bar;
-    int next_pos;
+    int next_chunk;
+    int front;                          /* positions [0, front) are linked (written by the build warp) */
     uint32_t red_a[32];
     unsigned long long red_b[32];
 };
 
 /*
- * One CTA per segment.  For every position p of the segment computes the
- * candidate token the greedy parse would emit if p were a parse head:
- *   M(p) = longest match among q in [max(lo, p - window), p - 1], ties -> nearest,
- *          capped at min(258, seg_hi - p); a literal if that is < 3.
- * This is process_loop's chain walk (src/deflate_compress.c:244-263) and
- * check_dup_str (:164-180) evaluated for all positions at once: because every
- * position enters the index (:313-318) and chains are walked to the end (:249),
- * M(p) is a pure function of the bytes.
+ * One CTA per segment: process_loop's match search AND its greedy token
+ * decision (src/deflate_compress.c:243-288), parallel yet exact.
+ *
+ * The longest / nearest match M(p) = argmax_{q in [max(lo, p-window), p-1]} lcp(q, p)
+ * (ties -> nearest, capped at min(258, seg_hi - p)) is a pure function of the
+ * bytes, because every position enters the index (:313-318) and chains are walked
+ * to the end (:249).  Only parse heads need it.  The segment is cut into 32-byte
+ * chunks; every lane takes a chunk, parses greedily from the chunk start as if it
+ * were a head (:265-288: len >= 3 -> advance len, else literal, advance 1) and
+ * KEEPS GOING past the chunk end until it steps on a position another lane has
+ * already claimed (shared bitmap, atomicOr) or leaves the segment.  By induction
+ * from position 0 (claimed by chunk 0's lane) every head of the true greedy parse
+ * is claimed and evaluated; speculative parses re-synchronise with the true one
+ * within a few tokens, so the extra work is small.  k_parse then follows the
+ * evaluated heads.  M(p) itself walks the bucket chain newest -> oldest out of
+ * shared memory (:244-263) with check_dup_str (:164-180) done 4 bytes at a time.
  */
 __global__ void __launch_bounds__(MATCH_THREADS, 1)
 k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, long long seg0,
@@ -197,7 +212,8 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     const uint32_t soff = 16 + (uint32_t)((uintptr_t)g0 & 15); /* data byte i lives at smem byte soff + i */
     uint8_t *sd = reinterpret_cast<uint8_t *>(S.data);
 
-    /* ---- stage [window | segment] into shared memory ---- */
+    const long long t0 = clock64();
+    /* ---- stage [window | segment] into shared memory (TMA bulk copy for the aligned interior) ---- */
     {
         int head_n = (int)((16 - ((uintptr_t)g0 & 15)) & 15);
         if (head_n > npos) head_n = npos;
@@ -205,9 +221,11 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         int tail0 = head_n + bulk_n;
         if (tid == 0) {
             mbar_init(&S.bar, 1);
-            S.next_pos = 0;
+            S.next_chunk = 0;
+            S.front = 0;
         }
         for (int i = tid; i < HASH_SIZE / 2; i += MATCH_THREADS) reinterpret_cast<uint32_t *>(S.head)[i] = 0xFFFFFFFFu;
+        for (int i = tid; i < DFL_MAX_SEG / 32; i += MATCH_THREADS) S.claimed[i] = 0;
         if (tid < 4) S.data[tid] = 0;
         __syncthreads();
         if (tid == 0 && bulk_n > 0) {
@@ -219,137 +237,224 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         }
         if (tid < head_n) sd[soff + tid] = g0[tid];
         for (int i = tail0 + tid; i < npos; i += MATCH_THREADS) sd[soff + i] = g0[i];
-        /* zero slack after the data so that over-reads compare unequal-or-zero deterministically */
-        if (tid < 32) sd[soff + npos + tid] = 0;
+        if (tid < 32) sd[soff + npos + tid] = 0; /* zero slack: over-reads past the data are deterministic */
         if (bulk_n > 0) mbar_wait(&S.bar, 0);
         __syncthreads();
     }
 
-    /* ---- Adler-32 partial sums of the segment bytes ---- */
-    {
-        uint32_t a = 0;
-        unsigned long long b = 0;
-        for (int i = tid; i < seglen; i += MATCH_THREADS) {
-            uint32_t v = sd[soff + hist + i];
-            a += v;
-            b += (unsigned long long)v * (uint32_t)(seglen - i);
+    const long long t1 = clock64();
+    long long t2 = t1;
+    if (warp == BUILD_WARP) {
+        /* ---- link every position into its bucket chain, in position order ----
+         * Same structure as dup_ht / dup_entries (src/deflate_compress.c:64-67,
+         * :313-318) with backward deltas.  One warp, 32 positions per step, runs
+         * concurrently with the parsers below, which only touch positions behind
+         * S.front.  Two positions of one step that share a bucket are detected by
+         * reading the head back after the store (the loser of the store race sees a
+         * foreign value); the check is done one step late so its latency is hidden,
+         * and the rare conflicts are resolved group by group with ballots.  The warp
+         * stays converged, so its shared-memory accesses are performed in program
+         * order (volatile keeps the compiler from forwarding or reordering them). */
+        volatile uint16_t *vhead = S.head;
+        volatile uint16_t *vdelta = S.delta;
+        volatile int *vfront = &S.front;
+        const int last = npos - 3; /* positions with 3 bytes available */
+        if (last >= 0) {
+            const int niter = last / 32 + 1;
+            const uint32_t lt = lanemask_lt();
+            uint32_t w_nx = (lane <= last) ? ld4(S.data, soff + lane) : 0;
+            bool pv = false;
+            int pp = 0, pbase = 0;
+            uint32_t ph = 0, pprev = 0xFFFFu, prb = 0;
+#pragma unroll 1
+            for (int it = 0; it <= niter; it++) {
+                const int base = it * 32, p = base + lane;
+                const bool v = it < niter && p <= last;
+                const uint32_t h = DFL_HASH3(w_nx);
+                w_nx = (p + 32 <= last) ? ld4(S.data, soff + p + 32) : 0; /* next step's bytes */
+                uint32_t prev = 0xFFFFu;
+                if (v) prev = vhead[h];
+                /* previous step: did two of its positions share a bucket? */
+                uint32_t losers = __ballot_sync(FULL, pv && prb != (uint32_t)pp);
+                if (losers) {
+                    while (losers) {
+                        const int L = __ffs(losers) - 1;
+                        const uint32_t hL = __shfl_sync(FULL, ph, L);
+                        const bool mine = pv && ph == hL;
+                        const uint32_t grp = __ballot_sync(FULL, mine);
+                        if (mine) {
+                            const uint32_t lower = grp & lt;
+                            if (lower) pprev = pbase + (31 - __clz(lower));
+                            if ((grp >> lane) == 1u) vhead[ph] = (uint16_t)pp; /* newest of its group */
+                        }
+                        losers &= ~grp;
+                    }
+                    if (v) prev = vhead[h]; /* heads changed under this step's read */
+                }
+                if (pv) vdelta[pp] = (pprev == 0xFFFFu) ? 0 : (uint16_t)(pp - pprev);
+                if (it > 0 && lane == 0) *vfront = base; /* steps < it are final */
+                uint32_t rb = (uint32_t)p;
+                if (v) {
+                    vhead[h] = (uint16_t)p;
+                    rb = vhead[h];
+                }
+                pv = v; pp = p; pbase = base; ph = h; pprev = prev; prb = rb;
+            }
         }
-        for (int o = 16; o; o >>= 1) {
-            a += __shfl_xor_sync(FULL, a, o);
-            b += __shfl_xor_sync(FULL, b, o);
-        }
-        if (lane == 0) { S.red_a[warp] = a; S.red_b[warp] = b; }
-        __syncthreads();
-        if (warp == 0) {
-            a = S.red_a[lane];
-            b = S.red_b[lane];
+        __syncwarp();
+        if (lane == 0) *vfront = 0x7FFFFFFF;
+        t2 = clock64();
+    } else {
+        /* ---- Adler-32 partial sums of the segment bytes ---- */
+        {
+            uint32_t a = 0;
+            unsigned long long b = 0;
+            for (int i = tid; i < seglen; i += MATCH_THREADS - 32) {
+                uint32_t v = sd[soff + hist + i];
+                a += v;
+                b += (unsigned long long)v * (uint32_t)(seglen - i);
+            }
             for (int o = 16; o; o >>= 1) {
                 a += __shfl_xor_sync(FULL, a, o);
                 b += __shfl_xor_sync(FULL, b, o);
             }
-            if (lane == 0) {
-                /* s1 += A ; s2 += B + A * (bytes after this segment)   (mod 65521) */
-                unsigned long long am = a % ADLER_MOD;
-                unsigned long long rest = (unsigned long long)(n - seg_hi) % ADLER_MOD;
-                unsigned long long bm = (b % ADLER_MOD + am * rest) % ADLER_MOD;
-                atomicAdd(&state->adl_a, am);
-                atomicAdd(&state->adl_b, bm);
-            }
+            if (lane == 0) { S.red_a[warp] = a; S.red_b[warp] = b; }
         }
-    }
 
-    /* ---- link every position into its bucket chain (one warp, position order) ----
-     * Same structure as the reference's dup_ht / dup_entries (src/deflate_compress.c:
-     * 64-67, :313-318), with backward deltas instead of ring indices. */
-    if (warp == 0) {
-        const int last = npos - 3; /* positions with 3 bytes available */
-        for (int base = 0; base <= last; base += 32) {
-            int p = base + lane;
-            bool valid = p <= last;
-            uint32_t h = valid ? DFL_HASH3(ld4(S.data, soff + p)) : (0x80000000u | lane);
-            uint32_t grp = __match_any_sync(FULL, h);
-            uint32_t lower = grp & lanemask_lt();
-            uint32_t prev = 0xFFFFu;
-            if (valid) {
-                if (lower) prev = base + (31 - __clz(lower));
-                else prev = S.head[h];
-            }
-            __syncwarp();
-            if (valid) {
-                S.delta[p] = (prev == 0xFFFFu) ? 0 : (uint16_t)(p - prev);
-                if ((grp >> lane) == 1u) S.head[h] = (uint16_t)p; /* newest of its group */
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-
-    /* ---- per-position longest match: persistent lanes over a block-wide counter ---- */
-    {
+        /* ---- speculative chunk parsers ---- */
+        enum { ST_IDLE = 0, ST_WALK = 1, ST_CAND = 2, ST_DONE = 3, ST_WAIT = 4 };
         const int W = prm.window, K = prm.chain_limit;
+        const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
+        const uint32_t lt = lanemask_lt();
+        volatile int *vfront = &S.front;
         uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
-        bool active = false, exhausted = false;
-        int p = 0, qi = 0, dist = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
-        uint32_t w0 = 0, pb = 0;
+        int st = ST_IDLE;
+        bool exhausted = false;
+        int i = 0, p = 0, qi = 0, dist = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
+        uint32_t pw0 = 0, pw1 = 0, pb = 0;
+
+        /* take position i_ as a parse head (caller has claimed it); the walk starts
+         * once the build warp has linked it */
+#define INIT_HEAD(i_)                                                                   \
+        do {                                                                            \
+            i = (i_);                                                                   \
+            p = hist + i;                                                               \
+            maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;           \
+            best_len = 2; best_dist = 0; dist = 0; hops = 0; qi = p;                    \
+            st = maxlen < DFL_MIN_MATCH ? ST_DONE : ST_WAIT;                            \
+        } while (0)
+
         for (;;) {
-            uint32_t idle = __ballot_sync(FULL, !active);
-            if (idle == FULL && exhausted) break;
-            if (!exhausted && (__popc(idle) >= REFILL_MIN_IDLE)) {
-                int cnt = __popc(idle), basep = 0;
-                if (lane == 0) basep = atomicAdd(&S.next_pos, cnt);
-                basep = __shfl_sync(FULL, basep, 0);
-                if (basep + cnt >= seglen) exhausted = true;
-                if (!active) {
-                    int i = basep + __popc(idle & lanemask_lt());
-                    if (i < seglen) {
-                        p = hist + i;
-                        maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;
-                        if (maxlen < DFL_MIN_MATCH) {
-                            out[i] = sd[soff + p];
-                        } else {
-                            active = true;
-                            qi = p; dist = 0; best_len = 2; best_dist = 0; hops = 0;
-                            w0 = ld4(S.data, soff + p) & 0xFFFFFFu;
-                        }
-                    }
+            if (st == ST_WAIT && p < *vfront) {
+                st = ST_WALK;
+                pw0 = ld4(S.data, soff + p);
+                pw1 = ld4(S.data, soff + p + 4);
+                pb = (pw0 >> 16) & 0xFF;
+            }
+            /* phase A: walk the chain until a candidate passes the one-byte filter */
+            if (st == ST_WALK) {
+#pragma unroll 1
+                for (int k = 0; k < HOP_BATCH; k++) {
+                    const uint32_t d = S.delta[qi];
+                    dist += d;
+                    qi -= d;
+                    if (d == 0 || dist > W || (K && hops >= K)) { st = ST_DONE; break; }
+                    hops++;
+                    if (sd[soff + qi + best_len] == pb) { st = ST_CAND; break; }
                 }
             }
-            if (active) {
-                bool done = false;
-                uint32_t d = S.delta[qi];
-                dist += d;
-                qi -= d;
-                if (d == 0 || dist > W || (K && hops >= K)) {
-                    done = true;
+            /* phase B: full compare (check_dup_str) for the lanes holding a candidate */
+            if (st == ST_CAND) {
+                int len;
+                uint32_t x = ld4(S.data, soff + qi) ^ pw0;
+                if (x) {
+                    len = (__ffs(x) - 1) >> 3;
                 } else {
-                    hops++;
-                    bool cand;
-                    if (best_len == 2) cand = ((ld4(S.data, soff + qi) & 0xFFFFFFu) == w0);
-                    else cand = (sd[soff + qi + best_len] == pb);
-                    if (cand) {
-                        int len = 0;
+                    x = ld4(S.data, soff + qi + 4) ^ pw1;
+                    if (x) {
+                        len = 4 + ((__ffs(x) - 1) >> 3);
+                    } else {
+                        len = 8;
                         while (len < maxlen) {
-                            uint32_t x = ld4(S.data, soff + p + len) ^ ld4(S.data, soff + qi + len);
+                            x = ld4(S.data, soff + p + len) ^ ld4(S.data, soff + qi + len);
                             if (x) { len += (__ffs(x) - 1) >> 3; break; }
                             len += 4;
                         }
-                        if (len > maxlen) len = maxlen;
-                        if (len > best_len) {
-                            best_len = len;
-                            best_dist = dist;
-                            if (len == maxlen) done = true;
-                            else pb = sd[soff + p + len];
+                    }
+                }
+                if (len > maxlen) len = maxlen;
+                st = ST_WALK;
+                if (len > best_len) {
+                    best_len = len;
+                    best_dist = dist;
+                    if (len == maxlen) st = ST_DONE;
+                    else pb = sd[soff + p + len];
+                }
+            }
+            /* phase C: finished heads emit their token and move on; idle lanes take new chunks */
+            const uint32_t m_done = __ballot_sync(FULL, st == ST_DONE);
+            const uint32_t m_idle = __ballot_sync(FULL, st == ST_IDLE);
+            const int ready = __popc(m_done) + (exhausted ? 0 : __popc(m_idle));
+            if (ready >= (exhausted ? 1 : REFILL_MIN_IDLE) || (m_done | m_idle) == FULL) {
+                if (st == ST_DONE) {
+                    int adv = 1;
+                    uint32_t t = sd[soff + p];
+                    if (best_len >= DFL_MIN_MATCH) {
+                        t = ((uint32_t)best_dist << 16) | (uint32_t)best_len;
+                        adv = best_len;
+                    }
+                    out[i] = t;
+                    st = ST_IDLE;
+                    const int ni = i + adv;
+                    if (ni < seglen) {
+                        const uint32_t bit = 1u << (ni & 31);
+                        if (!(atomicOr(&S.claimed[ni >> 5], bit) & bit)) INIT_HEAD(ni);
+                    }
+                }
+                const uint32_t idle = __ballot_sync(FULL, st == ST_IDLE);
+                if (idle && !exhausted) {
+                    const int cnt = __popc(idle);
+                    int basec = 0;
+                    if (lane == 0) basec = atomicAdd(&S.next_chunk, cnt);
+                    basec = __shfl_sync(FULL, basec, 0);
+                    if (basec + cnt >= nchunks) exhausted = true;
+                    if (st == ST_IDLE) {
+                        const int c = basec + __popc(idle & lt);
+                        if (c < nchunks) {
+                            const int ci = c * MATCH_CHUNK;
+                            const uint32_t bit = 1u << (ci & 31);
+                            if (!(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
                         }
                     }
                 }
-                if (done) {
-                    out[p - hist] = best_len >= DFL_MIN_MATCH ? ((uint32_t)best_dist << 16) | (uint32_t)best_len
-                                                              : (uint32_t)sd[soff + p];
-                    active = false;
-                }
+                if (exhausted && __ballot_sync(FULL, st != ST_IDLE) == 0) break;
+            } else if (__ballot_sync(FULL, st == ST_WALK || st == ST_CAND) == 0) {
+                __nanosleep(200); /* everyone here waits for the build warp */
             }
         }
+#undef INIT_HEAD
     }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = lane < BUILD_WARP ? S.red_a[lane] : 0;
+        unsigned long long b = lane < BUILD_WARP ? S.red_b[lane] : 0;
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(FULL, a, o);
+            b += __shfl_xor_sync(FULL, b, o);
+        }
+        if (lane == 0) {
+            /* s1 += A ; s2 += B + A * (bytes after this segment)   (mod 65521) */
+            unsigned long long am = a % ADLER_MOD;
+            unsigned long long rest = (unsigned long long)(n - seg_hi) % ADLER_MOD;
+            unsigned long long bm = (b % ADLER_MOD + am * rest) % ADLER_MOD;
+            atomicAdd(&state->adl_a, am);
+            atomicAdd(&state->adl_b, bm);
+            const long long t3 = clock64();
+            atomicAdd(&state->t_phase[0], (unsigned long long)(t1 - t0));
+            atomicAdd(&state->t_phase[3], (unsigned long long)(t3 - t0));
+        }
+    }
+    if (tid == BUILD_WARP * 32) atomicAdd(&state->t_phase[1], (unsigned long long)(t2 - t1));
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1343,6 +1448,12 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
 }
 
 extern "C" long dfl_b200_num_segments(dfl_ctx *ctx) { return ctx ? ctx->nseg_kept : 0; }
+
+/* k_match SM cycles of the last call, summed over CTAs: 0 stage-in, 1 build, 2 search, 3 total */
+extern "C" unsigned long long dfl_b200_phase_cycles(dfl_ctx *ctx, int k)
+{
+    return (ctx && k >= 0 && k < 4) ? ctx->h_state->t_phase[k] : 0;
+}
 
 extern "C" int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info)
 {

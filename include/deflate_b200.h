@@ -37,9 +37,9 @@ extern "C" {
 #define DFL_MAX_MATCH 258     /* src/include/deflate.h:4 */
 #define DFL_MAX_WINDOW 32768  /* README.md:6 */
 #define DFL_MAX_SEG 32768     /* one segment = one CTA-resident window pair */
-#define DFL_HASH_BITS 14      /* bucket hash width; observable only with chain_limit > 0 */
-/* bucket of the 3 bytes packed little-endian in v (low 24 bits) */
-#define DFL_HASH3(v) ((((uint32_t)(v) & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - DFL_HASH_BITS))
+#define DFL_HASH_BUCKETS 15360 /* bucket count (sized to the shared-memory budget); observable only with chain_limit > 0 */
+/* bucket of the 3 bytes packed little-endian in v (low 24 bits): multiplicative hash, range-reduced by mul-hi */
+#define DFL_HASH3(v) ((uint32_t)(((uint64_t)((((uint32_t)(v)) & 0xFFFFFFu) * 0x9E3779B1u) * DFL_HASH_BUCKETS) >> 32))
 
 /* error codes: 0 ok, negative on error (reference convention: callers test < 0,
  * src/png/png_decoder.c:249).  Values reuse src/include/global_errors.h:24-35. */
@@ -120,6 +120,10 @@ int dfl_b200_enable_timing(dfl_ctx *ctx, int enable);
 int dfl_b200_num_kernels(void);
 const char *dfl_b200_kernel_name(int k);
 double dfl_b200_kernel_ms(dfl_ctx *ctx, int k);
+
+/* k_match SM cycles of the last call summed over its CTAs: 0 stage-in, 1 chain build,
+ * 2 search, 3 total (profiling aid). */
+unsigned long long dfl_b200_phase_cycles(dfl_ctx *ctx, int k);
 
 /* Synthetic corpora generated on the device (bench/test support). */
 int dfl_b200_synth_random(uint8_t *d_out, size_t n, uint64_t seed, void *stream);

@@ -37,7 +37,7 @@ void orc_default_params(orc_params *p)
 uint32_t orc_hash3(const uint8_t *p)
 {
     uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-    return (v * 0x9E3779B1u) >> (32 - ORC_HASH_BITS);
+    return (uint32_t)(((uint64_t)(v * 0x9E3779B1u) * ORC_HASH_BUCKETS) >> 32);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -84,10 +84,10 @@ long orc_lz77_segment(const uint8_t *buf, long hist_lo, long seg_lo, long seg_hi
     span = seg_hi - hist_lo;
     if (span <= 0) return 0;
 
-    head = (int32_t *)malloc(sizeof(int32_t) << ORC_HASH_BITS);
+    head = (int32_t *)malloc(sizeof(int32_t) * ORC_HASH_BUCKETS);
     prev = (int32_t *)malloc(sizeof(int32_t) * (size_t)span);
     if (!head || !prev) { free(head); free(prev); return -1; }
-    for (i = 0; i < (1L << ORC_HASH_BITS); i++) head[i] = -1;
+    for (i = 0; i < ORC_HASH_BUCKETS; i++) head[i] = -1;
 
 #define ORC_INSERT(pos)                                              \
     do {                                                             \

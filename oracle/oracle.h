@@ -32,7 +32,7 @@ extern "C" {
 #define ORC_NUM_LL 286      /* src/include/deflate.h:5 */
 #define ORC_NUM_D 30        /* src/include/deflate.h:6 */
 #define ORC_NUM_CL 19
-#define ORC_HASH_BITS 14    /* bucket hash; only observable when chain_limit > 0 */
+#define ORC_HASH_BUCKETS 15360 /* bucket hash range; only observable when chain_limit > 0 */
 
 /* Token encoding shared with the CUDA path: literal -> byte value (dist field 0);
  * match -> (dist << 16) | len, len 3..258, dist 1..32768. */

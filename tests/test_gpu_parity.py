@@ -107,7 +107,7 @@ def test_params(D, O, prm):
 
 def test_mixed_blocks(D, O):
     """Text, random and zero stripes: stored, dynamic (and possibly fixed) blocks in one stream."""
-    parts = [make_input("markov", 1, 0, 40000), make_input("random", 4, 0, 50000), make_input("zeros", 0, 0, 70000),
+    parts = [make_input("markov", 1, 0, 40000), make_input("random", 4, 0, 100000), make_input("zeros", 0, 0, 70000),
              make_input("markov", 2, 0, 20), make_input("random", 9, 0, 40)]
     data = np.concatenate(parts)
     comp = D.Compressor()

@@ -23,8 +23,10 @@ def run(name, data, reps=3, **prm):
         out_len, adler = comp.finish(st)
         ms = e0.elapsed_time(e1)
         if best is None or ms < best[0]:
-            best = (ms, comp.kernel_ms())
-    ms, k = best
+            best = (ms, comp.kernel_ms(), comp.phase_cycles())
+    ms, k, ph = best
+    nseg = (data.size + 32767) // 32768
+    print("   per-segment k_match cycles: " + " ".join(f"{a}={b/nseg:.0f}" for a, b in ph.items()))
     print(f"{name:28s} n={data.size>>20:5d} MiB out={out_len/data.size:.4f} {ms:9.2f} ms {data.size/ms/1e6:8.2f} GB/s  " +
           " ".join(f"{a}={b:.2f}" for a, b in k.items()), flush=True)
     comp.close()
@@ -34,6 +36,7 @@ if __name__ == "__main__":
     n = mb << 20
     run("markov", synth.markov(n, 2))
     run("markov chain_limit=16", synth.markov(n, 2), chain_limit=16)
+    run("markov chain_limit=4", synth.markov(n, 2), chain_limit=4)
     run("markov window=4096", synth.markov(n, 2), window=4096)
     run("log", synth.log(n, 3))
     run("random", synth.random_bytes(n, 4))
