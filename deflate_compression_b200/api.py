@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
         L.dfl_b200_kernel_ms.argtypes = [vp, C.c_int]
         L.dfl_b200_phase_cycles.restype = C.c_uint64
         L.dfl_b200_phase_cycles.argtypes = [vp, C.c_int]
+        L.dfl_b200_sort_fallbacks.restype = C.c_uint
+        L.dfl_b200_sort_fallbacks.argtypes = [vp]
         L.dfl_b200_synth_random.argtypes = [vp, C.c_size_t, C.c_uint64, vp]
         # reference API (include/deflate_ext.h)
         L.deflate_compress.restype = C.c_int
@@ -219,8 +221,11 @@ class Compressor:
                 for k in range(L.dfl_b200_num_kernels())}
 
     def phase_cycles(self) -> dict:
-        names = ("stage_in", "build", "search", "total")
+        names = ("stage_in", "build", "search", "total", "sort1", "park", "sort2", "offsets", "d8", "d9", "d10", "d11")
         return {nm: int(lib().dfl_b200_phase_cycles(self._ctx, k)) for k, nm in enumerate(names)}
+
+    def sort_fallbacks(self) -> int:
+        return int(lib().dfl_b200_sort_fallbacks(self._ctx))
 
     def kernel_launches(self) -> int:
         return int(lib().dfl_b200_kernel_launches(self._ctx))

@@ -54,7 +54,8 @@ struct DevState {
     unsigned long long adl_b;      /* sum of per-segment weighted sums */
     unsigned int error;            /* 1 = output overflow */
     unsigned int adler;            /* final Adler-32 */
-    unsigned long long t_phase[4]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
+    unsigned long long t_phase[12]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
+    unsigned int sort_fallbacks;   /* segments whose index had to be rebuilt with the ballot-ranked scatter */
 };
 
 struct SegArrays {
@@ -157,42 +158,240 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 /* ------------------------------------------------------------------------- */
 
 #define MATCH_CHUNK 32   /* positions per speculative parse chunk */
-#define HOP_BATCH 8      /* chain hops a lane takes before the warp re-converges */
-#define BUILD_WARP (MATCH_THREADS / 32 - 1)
+#define HOP_BATCH 8      /* bucket entries a lane visits before the warp re-converges */
+#define COOP_MIN 64      /* buckets longer than this are walked by the whole warp */
+#define SORT_WARPS 32    /* every warp sorts one stripe */
+#define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
+#define SCRATCH_SLOTS 256
 
 struct MatchSmem {
     uint32_t data[(NPOS_MAX + 64) / 4]; /* [window | segment] bytes, 16 B of slack either side */
-    uint16_t delta[NPOS_MAX];           /* distance to the previous position of the same bucket, 0 = none */
-    uint16_t head[HASH_SIZE];           /* newest position of each bucket, 0xFFFF = empty */
-    uint32_t claimed[DFL_MAX_SEG / 32]; /* segment positions some lane has taken as a parse head */
+    uint16_t list[NPOS_MAX];            /* positions sorted by (bucket, position) */
+    uint16_t off[HASH_SIZE + 2];        /* bucket b owns list[off[b], off[b+1]); radix-sort counters during the build */
+    uint32_t claimed[DFL_MAX_SEG / 32]; /* positions some lane has taken as a parse head */
     uint64_t bar;
     int next_chunk;
-    int front;                          /* positions [0, front) are linked (written by the build warp) */
     uint32_t red_a[32];
     unsigned long long red_b[32];
+    uint32_t scan_w[32];
+    uint32_t scan_total;
 };
+
+/* exclusive block scan of one value per thread (all MATCH_THREADS threads call) */
+__device__ __forceinline__ uint32_t block_excl_scan(MatchSmem &S, uint32_t v, int lane, int warp)
+{
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) S.scan_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = S.scan_w[lane], u = t;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(FULL, u, o);
+            if (lane >= o) u += y;
+        }
+        S.scan_w[lane] = u - t;
+    }
+    __syncthreads();
+    uint32_t r = S.scan_w[warp] + x - v;
+    __syncthreads();
+    return r;
+}
+
+/* (digit, stripe) counter of the radix passes: u16, two per 32-bit word, parked in S.off
+ * (free until the offsets are written).  Stripe-major layout so that the lanes of a warp
+ * (one stripe, many digits) spread over the banks. */
+__device__ __forceinline__ uint32_t cnt_word(uint32_t stripe, uint32_t d) { return (stripe * SORT_BINS + d) >> 1; }
+__device__ __forceinline__ uint32_t cnt_shift(uint32_t d) { return (d & 1) * 16; }
+
+/*
+ * Scatter sweep of a sort warp over its stripe, 32 elements per step, 4 steps per
+ * round, in order.  PASS 1 reads positions in natural order, PASS 2 the pass-1
+ * order parked in gbuf (one round of loads kept in flight).  The (digit, stripe)
+ * counters are running cursors.
+ *   FAST:  slot = atomicAdd(cursor, 1).  Lanes of one warp instruction that hit
+ *          the same shared-memory word are served in ascending lane order on this
+ *          chip (measured: 0 violations in 1.3e9 pairs, tools/micro/atom_order.cu),
+ *          which makes the scatter stable.  It is not an architectural guarantee,
+ *          so the result is verified afterwards and, if ever wrong, redone with
+ *   !FAST: lanes with the same digit found with 7 ballots; cursor + rank in the
+ *          group.  Stable by construction; several times slower (a vote costs ~3
+ *          cycles of a unit shared by the whole SM).
+ */
+template <int PASS, bool FAST>
+__device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k_lo, int k_hi, const uint16_t *gbuf,
+                                              int lane, int warp)
+{
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off);
+    volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(S.off);
+    const uint32_t lt = lanemask_lt();
+    uint32_t eq[4] = {0, 0, 0, 0};
+    if (PASS == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (k_lo + j * 32 + lane < k_hi) eq[j] = __ldcg(gbuf + k_lo + j * 32 + lane);
+    }
+    for (int k0 = k_lo; k0 < k_hi; k0 += 128) {
+        uint32_t e[4], d[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { /* bytes + bucket digit of the round's 4 steps: independent work first */
+            const int k = k0 + j * 32 + lane;
+            e[j] = PASS == 1 ? (uint32_t)k : eq[j];
+            if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
+            const uint32_t b = DFL_HASH3(ld4(S.data, soff + (k < k_hi ? e[j] : 0)));
+            d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j * 32 + lane;
+            if (k0 + j * 32 >= k_hi) break;
+            const bool valid = k < k_hi;
+            if (FAST) {
+                if (valid) {
+                    const uint32_t sh = cnt_shift(d[j]);
+                    const uint32_t slot = (atomicAdd(&cnt32[cnt_word(warp, d[j])], 1u << sh) >> sh) & 0xFFFF;
+                    S.list[slot] = (uint16_t)e[j];
+                }
+            } else {
+                uint32_t peers = __ballot_sync(FULL, valid);
+#pragma unroll
+                for (int bit = 0; bit < 7; bit++) {
+                    const uint32_t bal = __ballot_sync(FULL, (d[j] >> bit) & 1);
+                    peers &= ((d[j] >> bit) & 1) ? bal : ~bal;
+                }
+                if (valid) {
+                    const uint32_t ci = warp * SORT_BINS + d[j];
+                    const uint32_t base = cnt16[ci];
+                    if ((peers >> lane) == 1u) cnt16[ci] = (uint16_t)(base + __popc(peers)); /* top lane of the group */
+                    S.list[base + __popc(peers & lt)] = (uint16_t)e[j];
+                }
+            }
+        }
+    }
+}
+
+/*
+ * One stable counting-sort pass over the NI indexed positions, by a 7-bit digit
+ * of their bucket.  PASS 1: natural order -> S.list by the low digit.  PASS 2:
+ * the pass-1 order (parked linearly in gbuf, global scratch, L2 resident) ->
+ * S.list by the high digit.  After both passes S.list is ordered by
+ * (bucket, position).  Both scatters stay in shared memory.  The input is cut
+ * into one contiguous stripe per warp; counting is order free (shared memory
+ * atomics), the scatter of a stripe is done in order by its warp.
+ */
+template <int PASS, bool FAST>
+__device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, const uint16_t *gbuf, int tid, int lane, int warp)
+{
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off);
+    uint16_t *cnt16 = S.off;
+    const int SS = ((NI + SORT_WARPS * 32 - 1) / (SORT_WARPS * 32)) * 32; /* stripe length, multiple of 32 */
+
+    for (int i = tid; i < SORT_BINS * SORT_WARPS / 2; i += MATCH_THREADS) cnt32[i] = 0;
+    __syncthreads();
+    /* count: every thread takes 8 consecutive elements at a time */
+    for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
+        uint32_t ev[4] = {0, 0, 0, 0};
+        if (PASS == 2) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(gbuf + k8));
+            ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
+        }
+        const uint32_t sw = (uint32_t)(k8 / SS); /* 8 | SS: the 8 elements share a stripe */
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (k8 + j < NI) {
+                const uint32_t e = PASS == 1 ? (uint32_t)(k8 + j) : ((ev[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
+                const uint32_t b = DFL_HASH3(ld4(S.data, soff + e));
+                const uint32_t d = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
+                atomicAdd(&cnt32[cnt_word(sw, d)], 1u << cnt_shift(d));
+            }
+        }
+    }
+    __syncthreads();
+    /* exclusive scan in (digit, stripe) order: SORT_BINS * SORT_WARPS = 4096 u16 entries, 4 per thread */
+    {
+        const uint32_t d = tid / (SORT_WARPS / 4), s0 = (tid % (SORT_WARPS / 4)) * 4;
+        uint32_t c[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { c[j] = cnt16[(s0 + j) * SORT_BINS + d]; sum += c[j]; }
+        uint32_t base = block_excl_scan(S, sum, lane, warp);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { cnt16[(s0 + j) * SORT_BINS + d] = (uint16_t)base; base += c[j]; }
+    }
+    __syncthreads();
+    {
+        const int k_lo = warp * SS, k_hi = (k_lo + SS < NI) ? k_lo + SS : NI;
+        scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, gbuf, lane, warp);
+    }
+    __syncthreads();
+}
+
+/* Sort the NI indexed positions by (bucket, position) into S.list and fill the
+ * bucket offsets.  Returns (to every thread) whether the order verified. */
+template <bool FAST>
+__device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI, uint16_t *gbuf, int tid, int lane, int warp,
+                                            DevState *state)
+{
+    long long c0 = clock64(), c1;
+#define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
+    sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp);
+    STAMP(4);
+    /* park the pass-1 order in global scratch: linear, 16 B per thread */
+    for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8)
+        __stcg(reinterpret_cast<uint4 *>(gbuf + k8), *reinterpret_cast<const uint4 *>(&S.list[k8]));
+    STAMP(5);
+    sort_pass<2, FAST>(S, soff, NI, gbuf, tid, lane, warp);
+    STAMP(6);
+    /* bucket offsets from the sorted order (off[b] = first slot whose bucket is >= b), and
+     * the check that every bucket is in ascending position order.  Slot kk is compared with
+     * slot kk-1; consecutive threads take consecutive slots. */
+    bool bad = false;
+    if (NI == 0) {
+        for (int i = tid; i < HASH_SIZE + 2; i += MATCH_THREADS) S.off[i] = 0;
+    }
+    for (int kk = tid; kk < NI + 1; kk += MATCH_THREADS) {
+        const int q = kk < NI ? (int)S.list[kk] : 0;
+        const int b = kk < NI ? (int)DFL_HASH3(ld4(S.data, soff + q)) : HASH_SIZE;
+        const int pq = kk > 0 ? (int)S.list[kk - 1] : -1;
+        const int pb_ = kk > 0 ? (int)DFL_HASH3(ld4(S.data, soff + pq)) : -1;
+        bad |= kk < NI && ((b < pb_) || (b == pb_ && q <= pq));
+        for (int bb = pb_ + 1; bb <= b; bb++) S.off[bb] = (uint16_t)kk;
+    }
+    const bool ok = __syncthreads_or(bad) == 0;
+    STAMP(7);
+#undef STAMP
+    return ok;
+}
 
 /*
  * One CTA per segment: process_loop's match search AND its greedy token
  * decision (src/deflate_compress.c:243-288), parallel yet exact.
  *
- * The longest / nearest match M(p) = argmax_{q in [max(lo, p-window), p-1]} lcp(q, p)
- * (ties -> nearest, capped at min(258, seg_hi - p)) is a pure function of the
- * bytes, because every position enters the index (:313-318) and chains are walked
- * to the end (:249).  Only parse heads need it.  The segment is cut into 32-byte
- * chunks; every lane takes a chunk, parses greedily from the chunk start as if it
- * were a head (:265-288: len >= 3 -> advance len, else literal, advance 1) and
- * KEEPS GOING past the chunk end until it steps on a position another lane has
- * already claimed (shared bitmap, atomicOr) or leaves the segment.  By induction
- * from position 0 (claimed by chunk 0's lane) every head of the true greedy parse
- * is claimed and evaluated; speculative parses re-synchronise with the true one
- * within a few tokens, so the extra work is small.  k_parse then follows the
- * evaluated heads.  M(p) itself walks the bucket chain newest -> oldest out of
- * shared memory (:244-263) with check_dup_str (:164-180) done 4 bytes at a time.
+ * Index.  The reference threads every position onto the chain of its hash bucket
+ * (dup_ht / dup_entries, :64-67, :313-318) and walks a chain newest -> oldest
+ * (:249-263).  Here the same buckets are laid out as one array: all positions of
+ * [window | segment] sorted by (bucket, position) with a two-pass stable radix
+ * sort done by the whole CTA, plus bucket offsets.  Walking a bucket backwards
+ * from a position's own slot visits exactly the chain the reference walks, but
+ * the next candidate's address never depends on the previous load.
+ *
+ * Parse.  The longest / nearest match M(p) = argmax_{q in [max(lo, p-window), p-1]}
+ * lcp(q, p) (ties -> nearest, capped at min(258, seg_hi - p)) is a pure function of
+ * the bytes, because every position is indexed and buckets are walked to the end.
+ * Only parse heads need it.  The segment is cut into 32-byte chunks; every lane
+ * takes a chunk, parses greedily from the chunk start as if it were a head
+ * (:265-288: len >= 3 -> advance len, else literal, advance 1) and KEEPS GOING past
+ * the chunk end until it steps on a position another lane has already claimed
+ * (shared bitmap, atomicOr) or leaves the segment.  By induction from position 0
+ * (claimed by chunk 0's lane) every head of the true greedy parse is claimed and
+ * evaluated; speculative parses re-synchronise with the true one within a few
+ * tokens, so the extra work is small.  k_parse then follows the evaluated heads.
  */
 __global__ void __launch_bounds__(MATCH_THREADS, 1)
 k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, long long seg0,
-        dfl_params prm, uint32_t *__restrict__ tokcand, DevState *state)
+        dfl_params prm, uint32_t *__restrict__ tokcand, uint16_t *__restrict__ scratch, DevState *state)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MatchSmem &S = *reinterpret_cast<MatchSmem *>(smem_raw);
@@ -222,9 +421,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         if (tid == 0) {
             mbar_init(&S.bar, 1);
             S.next_chunk = 0;
-            S.front = 0;
         }
-        for (int i = tid; i < HASH_SIZE / 2; i += MATCH_THREADS) reinterpret_cast<uint32_t *>(S.head)[i] = 0xFFFFFFFFu;
         for (int i = tid; i < DFL_MAX_SEG / 32; i += MATCH_THREADS) S.claimed[i] = 0;
         if (tid < 4) S.data[tid] = 0;
         __syncthreads();
@@ -241,142 +438,116 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         if (bulk_n > 0) mbar_wait(&S.bar, 0);
         __syncthreads();
     }
-
     const long long t1 = clock64();
-    long long t2 = t1;
-    if (warp == BUILD_WARP) {
-        /* ---- link every position into its bucket chain, in position order ----
-         * Same structure as dup_ht / dup_entries (src/deflate_compress.c:64-67,
-         * :313-318) with backward deltas.  One warp, 32 positions per step, runs
-         * concurrently with the parsers below, which only touch positions behind
-         * S.front.  Two positions of one step that share a bucket are detected by
-         * reading the head back after the store (the loser of the store race sees a
-         * foreign value); the check is done one step late so its latency is hidden,
-         * and the rare conflicts are resolved group by group with ballots.  The warp
-         * stays converged, so its shared-memory accesses are performed in program
-         * order (volatile keeps the compiler from forwarding or reordering them). */
-        volatile uint16_t *vhead = S.head;
-        volatile uint16_t *vdelta = S.delta;
-        volatile int *vfront = &S.front;
-        const int last = npos - 3; /* positions with 3 bytes available */
-        if (last >= 0) {
-            const int niter = last / 32 + 1;
-            const uint32_t lt = lanemask_lt();
-            uint32_t w_nx = (lane <= last) ? ld4(S.data, soff + lane) : 0;
-            bool pv = false;
-            int pp = 0, pbase = 0;
-            uint32_t ph = 0, pprev = 0xFFFFu, prb = 0;
-#pragma unroll 1
-            for (int it = 0; it <= niter; it++) {
-                const int base = it * 32, p = base + lane;
-                const bool v = it < niter && p <= last;
-                const uint32_t h = DFL_HASH3(w_nx);
-                w_nx = (p + 32 <= last) ? ld4(S.data, soff + p + 32) : 0; /* next step's bytes */
-                uint32_t prev = 0xFFFFu;
-                if (v) prev = vhead[h];
-                /* previous step: did two of its positions share a bucket? */
-                uint32_t losers = __ballot_sync(FULL, pv && prb != (uint32_t)pp);
-                if (losers) {
-                    while (losers) {
-                        const int L = __ffs(losers) - 1;
-                        const uint32_t hL = __shfl_sync(FULL, ph, L);
-                        const bool mine = pv && ph == hL;
-                        const uint32_t grp = __ballot_sync(FULL, mine);
-                        if (mine) {
-                            const uint32_t lower = grp & lt;
-                            if (lower) pprev = pbase + (31 - __clz(lower));
-                            if ((grp >> lane) == 1u) vhead[ph] = (uint16_t)pp; /* newest of its group */
-                        }
-                        losers &= ~grp;
-                    }
-                    if (v) prev = vhead[h]; /* heads changed under this step's read */
-                }
-                if (pv) vdelta[pp] = (pprev == 0xFFFFu) ? 0 : (uint16_t)(pp - pprev);
-                if (it > 0 && lane == 0) *vfront = base; /* steps < it are final */
-                uint32_t rb = (uint32_t)p;
-                if (v) {
-                    vhead[h] = (uint16_t)p;
-                    rb = vhead[h];
-                }
-                pv = v; pp = p; pbase = base; ph = h; pprev = prev; prb = rb;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) *vfront = 0x7FFFFFFF;
-        t2 = clock64();
-    } else {
-        /* ---- Adler-32 partial sums of the segment bytes ---- */
-        {
-            uint32_t a = 0;
-            unsigned long long b = 0;
-            for (int i = tid; i < seglen; i += MATCH_THREADS - 32) {
-                uint32_t v = sd[soff + hist + i];
-                a += v;
-                b += (unsigned long long)v * (uint32_t)(seglen - i);
-            }
-            for (int o = 16; o; o >>= 1) {
-                a += __shfl_xor_sync(FULL, a, o);
-                b += __shfl_xor_sync(FULL, b, o);
-            }
-            if (lane == 0) { S.red_a[warp] = a; S.red_b[warp] = b; }
-        }
 
-        /* ---- speculative chunk parsers ---- */
-        enum { ST_IDLE = 0, ST_WALK = 1, ST_CAND = 2, ST_DONE = 3, ST_WAIT = 4 };
+    /* ---- Adler-32 partial sums of the segment bytes ---- */
+    {
+        uint32_t a = 0;
+        unsigned long long b = 0;
+        for (int i = tid; i < seglen; i += MATCH_THREADS) {
+            uint32_t v = sd[soff + hist + i];
+            a += v;
+            b += (unsigned long long)v * (uint32_t)(seglen - i);
+        }
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(FULL, a, o);
+            b += __shfl_xor_sync(FULL, b, o);
+        }
+        if (lane == 0) { S.red_a[warp] = a; S.red_b[warp] = b; }
+    }
+
+    /* ---- index: positions with 3 bytes available, sorted by (bucket, position) ---- */
+    const int NI = npos >= 3 ? npos - 2 : 0;
+    {
+        unsigned int smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        uint16_t *gbuf = scratch + (size_t)(smid % SCRATCH_SLOTS) * NPOS_MAX; /* one CTA per SM: private slot */
+        if (!build_index<true>(S, soff, NI, gbuf, tid, lane, warp, state)) {
+            /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
+            if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
+            build_index<false>(S, soff, NI, gbuf, tid, lane, warp, state);
+        }
+    }
+    const long long t2 = clock64();
+
+    /* ---- speculative chunk parsers ---- */
+    {
+        enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
         const int W = prm.window, K = prm.chain_limit;
         const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
-        const uint32_t lt = lanemask_lt();
-        volatile int *vfront = &S.front;
         uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
         int st = ST_IDLE;
-        bool exhausted = false;
-        int i = 0, p = 0, qi = 0, dist = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
-        uint32_t pw0 = 0, pw1 = 0, pb = 0;
+        int i = 0, p = 0, q = 0, k = 0, k_lo = 0, k_hi = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
+        uint32_t pw0 = 0, pw1 = 0, fword = 0, fmask = 0;
+        int foff = 0;
 
-        /* take position i_ as a parse head (caller has claimed it); the walk starts
-         * once the build warp has linked it */
+        /* take position i_ as a parse head (caller has claimed it) */
 #define INIT_HEAD(i_)                                                                   \
         do {                                                                            \
             i = (i_);                                                                   \
             p = hist + i;                                                               \
             maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;           \
-            best_len = 2; best_dist = 0; dist = 0; hops = 0; qi = p;                    \
-            st = maxlen < DFL_MIN_MATCH ? ST_DONE : ST_WAIT;                            \
+            best_len = 2; best_dist = 0; hops = 0;                                      \
+            if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                               \
+            else {                                                                      \
+                st = ST_SEEK;                                                           \
+                pw0 = ld4(S.data, soff + p);                                            \
+                pw1 = ld4(S.data, soff + p + 4);                                        \
+                foff = 0; fmask = 0xFFFFFFu; fword = pw0 & 0xFFFFFFu;                   \
+                const uint32_t b_ = DFL_HASH3(pw0);                                     \
+                k_lo = S.off[b_];                                                       \
+                k = k_lo;                                                               \
+                k_hi = S.off[b_ + 1];                                                   \
+            }                                                                           \
         } while (0)
 
         for (;;) {
-            if (st == ST_WAIT && p < *vfront) {
-                st = ST_WALK;
-                pw0 = ld4(S.data, soff + p);
-                pw1 = ld4(S.data, soff + p + 4);
-                pb = (pw0 >> 16) & 0xFF;
-            }
-            /* phase A: walk the chain until a candidate passes the one-byte filter */
-            if (st == ST_WALK) {
+            /* phase A: find the head's own slot in its bucket (lower bound of p in
+             * list[k, k_hi)), then walk the bucket backwards until a candidate passes
+             * the one-byte filter */
+            if (st == ST_SEEK || st == ST_WALK) {
 #pragma unroll 1
-                for (int k = 0; k < HOP_BATCH; k++) {
-                    const uint32_t d = S.delta[qi];
-                    dist += d;
-                    qi -= d;
-                    if (d == 0 || dist > W || (K && hops >= K)) { st = ST_DONE; break; }
-                    hops++;
-                    if (sd[soff + qi + best_len] == pb) { st = ST_CAND; break; }
+                for (int t = 0; t < HOP_BATCH; t++) {
+                    if (st == ST_SEEK) {
+                        if (k < k_hi) {
+                            const int mid = (k + k_hi) >> 1;
+                            if ((int)S.list[mid] < p) k = mid + 1; else k_hi = mid;
+                        } else {
+                            /* k is the slot of p; candidates are k-1 ... k_lo.  A long bucket is
+                             * walked by the whole warp together (phase C) */
+                            st = ST_WALK;
+                        }
+                    } else {
+                        if (k <= k_lo || (K && hops >= K)) { st = ST_DONE; break; }
+                        q = S.list[--k];
+                        if (p - q > W) { st = ST_DONE; break; }
+                        hops++;
+                        /* filter: the 4 bytes ending at offset best_len (the 3 of the trigram while
+                         * nothing is found yet) must match for q to beat the best so far */
+                        if ((ld4(S.data, soff + q + foff) & fmask) == fword) { st = ST_CAND; break; }
+                    }
                 }
+            }
+            /* a long remainder of the bucket is walked by the whole warp together (phase C) */
+            if (st == ST_WALK) {
+                int rem = k - k_lo;
+                if (K && K - hops < rem) rem = K - hops;
+                if (rem > COOP_MIN) st = ST_HEAVY;
             }
             /* phase B: full compare (check_dup_str) for the lanes holding a candidate */
             if (st == ST_CAND) {
                 int len;
-                uint32_t x = ld4(S.data, soff + qi) ^ pw0;
+                uint32_t x = ld4(S.data, soff + q) ^ pw0;
                 if (x) {
                     len = (__ffs(x) - 1) >> 3;
                 } else {
-                    x = ld4(S.data, soff + qi + 4) ^ pw1;
+                    x = ld4(S.data, soff + q + 4) ^ pw1;
                     if (x) {
                         len = 4 + ((__ffs(x) - 1) >> 3);
                     } else {
                         len = 8;
                         while (len < maxlen) {
-                            x = ld4(S.data, soff + p + len) ^ ld4(S.data, soff + qi + len);
+                            x = ld4(S.data, soff + p + len) ^ ld4(S.data, soff + q + len);
                             if (x) { len += (__ffs(x) - 1) >> 3; break; }
                             len += 4;
                         }
@@ -386,16 +557,77 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                 st = ST_WALK;
                 if (len > best_len) {
                     best_len = len;
-                    best_dist = dist;
+                    best_dist = p - q;
                     if (len == maxlen) st = ST_DONE;
-                    else pb = sd[soff + p + len];
+                    else { foff = len - 3; fmask = 0xFFFFFFFFu; fword = ld4(S.data, soff + p + foff); }
                 }
             }
-            /* phase C: finished heads emit their token and move on; idle lanes take new chunks */
-            const uint32_t m_done = __ballot_sync(FULL, st == ST_DONE);
-            const uint32_t m_idle = __ballot_sync(FULL, st == ST_IDLE);
-            const int ready = __popc(m_done) + (exhausted ? 0 : __popc(m_idle));
-            if (ready >= (exhausted ? 1 : REFILL_MIN_IDLE) || (m_done | m_idle) == FULL) {
+            /* phase C: finished heads emit their token and move on; idle lanes take new
+             * chunks.  One warp reduction per round steers it (votes and shuffles share a
+             * slow unit on this chip). */
+            const uint32_t census = __reduce_add_sync(FULL, (st == ST_SEEK || st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) |
+                                                                (st == ST_HEAVY ? 0x10000u : 0u));
+            const int n_busy = census & 0xFF, n_fin = (census >> 8) & 0xFF, n_heavy = census >> 16;
+            if (n_fin == 32) break;
+            if (n_heavy) {
+                /* cooperative walk: the 32 lanes take 32 consecutive bucket entries per pass,
+                 * nearest first; one warp reduction per pass picks the longest (then nearest)
+                 * improvement and tightens the filter for the next pass.  Same result as the
+                 * sequential walk: strict improvement only, nearer passes first. */
+                uint32_t heavy = __ballot_sync(FULL, st == ST_HEAVY);
+                while (heavy) {
+                    const int L = __ffs(heavy) - 1;
+                    heavy &= heavy - 1;
+                    const int hp = __shfl_sync(FULL, p, L), hk = __shfl_sync(FULL, k, L);
+                    int hlo = __shfl_sync(FULL, k_lo, L);
+                    const int hmax = __shfl_sync(FULL, maxlen, L);
+                    const uint32_t hw0 = __shfl_sync(FULL, pw0, L), hw1 = __shfl_sync(FULL, pw1, L);
+                    const int hhops = __shfl_sync(FULL, hops, L);
+                    if (K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
+                    int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
+                    int hfoff = hbest == 2 ? 0 : hbest - 3;
+                    uint32_t hfmask = hbest == 2 ? 0xFFFFFFu : 0xFFFFFFFFu;
+                    uint32_t hfword = ld4(S.data, soff + hp + hfoff) & hfmask;
+                    for (int top = hk; top > hlo; top -= 32) {
+                        const int kk = top - 1 - lane;
+                        bool valid = kk >= hlo;
+                        const int cq = valid ? (int)S.list[kk] : 0;
+                        valid = valid && (hp - cq <= W);
+                        uint32_t key = valid ? 0x80000000u : 0u;
+                        if (valid && (ld4(S.data, soff + cq + hfoff) & hfmask) == hfword) {
+                            int len;
+                            uint32_t x = ld4(S.data, soff + cq) ^ hw0;
+                            if (x) {
+                                len = (__ffs(x) - 1) >> 3;
+                            } else {
+                                x = ld4(S.data, soff + cq + 4) ^ hw1;
+                                if (x) {
+                                    len = 4 + ((__ffs(x) - 1) >> 3);
+                                } else {
+                                    len = 8;
+                                    while (len < hmax) {
+                                        x = ld4(S.data, soff + hp + len) ^ ld4(S.data, soff + cq + len);
+                                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                                        len += 4;
+                                    }
+                                }
+                            }
+                            if (len > hmax) len = hmax;
+                            if (len > hbest) key |= ((uint32_t)len << 16) | (uint32_t)(0xFFFF - (hp - cq));
+                        }
+                        const uint32_t kmax = __reduce_max_sync(FULL, key);
+                        if (!(kmax >> 31)) break; /* the whole pass is outside the window */
+                        if (kmax & 0x7FFFFFFFu) {
+                            hbest = (kmax >> 16) & 0x7FFF;
+                            hdist = 0xFFFF - (kmax & 0xFFFF);
+                            if (hbest == hmax) break;
+                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4(S.data, soff + hp + hfoff);
+                        }
+                    }
+                    if (lane == L) { best_len = hbest; best_dist = hdist; st = ST_DONE; }
+                }
+            }
+            if (32 - n_busy - n_fin >= REFILL_MIN_IDLE || n_busy == 0) {
                 if (st == ST_DONE) {
                     int adv = 1;
                     uint32_t t = sd[soff + p];
@@ -411,33 +643,24 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                         if (!(atomicOr(&S.claimed[ni >> 5], bit) & bit)) INIT_HEAD(ni);
                     }
                 }
-                const uint32_t idle = __ballot_sync(FULL, st == ST_IDLE);
-                if (idle && !exhausted) {
-                    const int cnt = __popc(idle);
-                    int basec = 0;
-                    if (lane == 0) basec = atomicAdd(&S.next_chunk, cnt);
-                    basec = __shfl_sync(FULL, basec, 0);
-                    if (basec + cnt >= nchunks) exhausted = true;
-                    if (st == ST_IDLE) {
-                        const int c = basec + __popc(idle & lt);
-                        if (c < nchunks) {
-                            const int ci = c * MATCH_CHUNK;
-                            const uint32_t bit = 1u << (ci & 31);
-                            if (!(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
-                        }
+                if (st == ST_IDLE) {
+                    const int c = atomicAdd(&S.next_chunk, 1);
+                    if (c >= nchunks) {
+                        st = ST_FIN;
+                    } else {
+                        const int ci = c * MATCH_CHUNK;
+                        const uint32_t bit = 1u << (ci & 31);
+                        if (!(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
                     }
                 }
-                if (exhausted && __ballot_sync(FULL, st != ST_IDLE) == 0) break;
-            } else if (__ballot_sync(FULL, st == ST_WALK || st == ST_CAND) == 0) {
-                __nanosleep(200); /* everyone here waits for the build warp */
             }
         }
 #undef INIT_HEAD
     }
     __syncthreads();
     if (warp == 0) {
-        uint32_t a = lane < BUILD_WARP ? S.red_a[lane] : 0;
-        unsigned long long b = lane < BUILD_WARP ? S.red_b[lane] : 0;
+        uint32_t a = S.red_a[lane];
+        unsigned long long b = S.red_b[lane];
         for (int o = 16; o; o >>= 1) {
             a += __shfl_xor_sync(FULL, a, o);
             b += __shfl_xor_sync(FULL, b, o);
@@ -451,10 +674,11 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             atomicAdd(&state->adl_b, bm);
             const long long t3 = clock64();
             atomicAdd(&state->t_phase[0], (unsigned long long)(t1 - t0));
+            atomicAdd(&state->t_phase[1], (unsigned long long)(t2 - t1));
+            atomicAdd(&state->t_phase[2], (unsigned long long)(t3 - t2));
             atomicAdd(&state->t_phase[3], (unsigned long long)(t3 - t0));
         }
     }
-    if (tid == BUILD_WARP * 32) atomicAdd(&state->t_phase[1], (unsigned long long)(t2 - t1));
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1080,6 +1304,7 @@ struct dfl_ctx {
     /* chunk workspace */
     size_t ws_segs, ws_seg_bytes;
     uint32_t *tokcand;
+    uint16_t *scratch; /* k_match radix-sort ping buffer, one slot per SM */
     SegArrays A;
     void *seg_blob;
     DevState *state;
@@ -1215,6 +1440,7 @@ extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
     }
     if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
         cudaMalloc(&ctx->state, sizeof(DevState)) != cudaSuccess ||
+        cudaMalloc(&ctx->scratch, (size_t)SCRATCH_SLOTS * NPOS_MAX * sizeof(uint16_t)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_state, sizeof(DevState)) != cudaSuccess) {
         free(ctx);
         return DFL_E_CUDA;
@@ -1229,6 +1455,7 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     cudaSetDevice(ctx->device);
     free_ws(ctx);
     if (ctx->state) cudaFree(ctx->state);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
@@ -1350,7 +1577,7 @@ extern "C" int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_
     for (size_t s0 = 0; s0 < nseg; s0 += chunk_segs) {
         int ns = (int)(nseg - s0 < chunk_segs ? nseg - s0 : chunk_segs);
         LAUNCH(K_MATCH, k_match, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
-               (long long)s0, prm, ctx->tokcand, ctx->state);
+               (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
         LAUNCH(K_PARSE, k_parse, (ns + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st, (long long)n,
                (long long)s0, ns, prm, ctx->tokcand, ctx->A);
         LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
@@ -1449,10 +1676,13 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
 
 extern "C" long dfl_b200_num_segments(dfl_ctx *ctx) { return ctx ? ctx->nseg_kept : 0; }
 
+/* segments of the last call whose index was rebuilt with the ballot-ranked scatter (expected 0) */
+extern "C" unsigned int dfl_b200_sort_fallbacks(dfl_ctx *ctx) { return ctx ? ctx->h_state->sort_fallbacks : 0; }
+
 /* k_match SM cycles of the last call, summed over CTAs: 0 stage-in, 1 build, 2 search, 3 total */
 extern "C" unsigned long long dfl_b200_phase_cycles(dfl_ctx *ctx, int k)
 {
-    return (ctx && k >= 0 && k < 4) ? ctx->h_state->t_phase[k] : 0;
+    return (ctx && k >= 0 && k < 12) ? ctx->h_state->t_phase[k] : 0;
 }
 
 extern "C" int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info)

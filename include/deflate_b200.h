@@ -124,6 +124,9 @@ double dfl_b200_kernel_ms(dfl_ctx *ctx, int k);
 /* k_match SM cycles of the last call summed over its CTAs: 0 stage-in, 1 chain build,
  * 2 search, 3 total (profiling aid). */
 unsigned long long dfl_b200_phase_cycles(dfl_ctx *ctx, int k);
+/* Segments of the last call whose index had to be rebuilt with the slow, ballot-ranked
+ * scatter because the fast atomic-ticket scatter failed its order check (expected 0). */
+unsigned int dfl_b200_sort_fallbacks(dfl_ctx *ctx);
 
 /* Synthetic corpora generated on the device (bench/test support). */
 int dfl_b200_synth_random(uint8_t *d_out, size_t n, uint64_t seed, void *stream);

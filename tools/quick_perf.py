@@ -24,9 +24,12 @@ def run(name, data, reps=3, **prm):
         ms = e0.elapsed_time(e1)
         if best is None or ms < best[0]:
             best = (ms, comp.kernel_ms(), comp.phase_cycles())
+        fb = comp.sort_fallbacks()
+        if fb:
+            print("   !! sort fallbacks:", fb)
     ms, k, ph = best
     nseg = (data.size + 32767) // 32768
-    print("   per-segment k_match cycles: " + " ".join(f"{a}={b/nseg:.0f}" for a, b in ph.items()))
+    print("   per-segment k_match cycles: " + " ".join(f"{a}={b/nseg:.0f}" for a, b in ph.items() if not a.startswith("d")))
     print(f"{name:28s} n={data.size>>20:5d} MiB out={out_len/data.size:.4f} {ms:9.2f} ms {data.size/ms/1e6:8.2f} GB/s  " +
           " ".join(f"{a}={b:.2f}" for a, b in k.items()), flush=True)
     comp.close()
