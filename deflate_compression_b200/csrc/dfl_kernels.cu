@@ -832,19 +832,23 @@ __device__ void huff_lengths_warp(const uint32_t *freq, int n, int limit, uint8_
         int bl[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) bl[i] = 0;
-        int overflow = 0;
         for (int i = 0; i < m; i++) {
             int d = sc.idepth[sc.lpar[i]] + 1;
-            if (d > limit) { d = limit; overflow++; }
-            bl[d]++;
+            bl[d > limit ? limit : d]++;
         }
-        while (overflow > 0) {
-            int bits = limit - 1;
-            while (bl[bits] == 0) bits--;
-            bl[bits]--;
-            bl[bits + 1] += 2;
+        /* Kraft repair in units of 2^-limit (same steps as the oracle) */
+        unsigned int kraft = 0;
+        for (int bits = 1; bits <= limit; bits++) kraft += (unsigned int)bl[bits] << (limit - bits);
+        while (kraft > (1u << limit)) {
             bl[limit]--;
-            overflow -= 2;
+            for (int bits = limit - 1; bits > 0; bits--) {
+                if (bl[bits]) {
+                    bl[bits]--;
+                    bl[bits + 1] += 2;
+                    break;
+                }
+            }
+            kraft--;
         }
         int j = 0;
         for (int bits = limit; bits >= 1; bits--)

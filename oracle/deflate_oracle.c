@@ -212,8 +212,8 @@ static int orc_dist_sym(int dist, int *ebits, int *eval)
  *      the reference, src/h_tree.c:257-259);
  *   2. sort by (weight asc, symbol asc);
  *   3. two-queue merge, ties -> leaf queue first;
- *   4. count leaves per depth, clip at `limit`, repair the Kraft sum by moving
- *      leaves down (the classic overflow repair published with zlib's trees.c);
+ *   4. count leaves per depth, clip at `limit`, repair the Kraft sum one unit of
+ *      2^-limit at a time by moving a leaf of the deepest shorter level down;
  *   5. hand lengths out along the sorted order, longest to the lightest.
  * Deterministic: the CUDA path must reproduce it bit for bit.
  */
@@ -224,7 +224,8 @@ void orc_huff_lengths(const uint32_t *freq, int n, int limit, uint8_t *len)
     uint32_t iw[ORC_NUM_LL + 2];
     int lpar[ORC_NUM_LL + 2], ipar[ORC_NUM_LL + 2], idepth[ORC_NUM_LL + 2];
     int bl_count[64];
-    int m = 0, s, i, j, li, ih, it, overflow, bits;
+    int m = 0, s, i, j, li, ih, it, bits;
+    unsigned long kraft;
 
     for (s = 0; s < n; s++) {
         len[s] = 0;
@@ -259,19 +260,26 @@ void orc_huff_lengths(const uint32_t *freq, int n, int limit, uint8_t *len)
     idepth[m - 2] = 0;
     for (i = m - 3; i >= 0; i--) idepth[i] = idepth[ipar[i]] + 1;
     memset(bl_count, 0, sizeof(bl_count));
-    overflow = 0;
     for (i = 0; i < m; i++) {
         int d = idepth[lpar[i]] + 1;
-        if (d > limit) { d = limit; overflow++; }
-        bl_count[d]++;
+        bl_count[d > limit ? limit : d]++;
     }
-    while (overflow > 0) {
-        bits = limit - 1;
-        while (bl_count[bits] == 0) bits--;
-        bl_count[bits]--;
-        bl_count[bits + 1] += 2;
+    /* Kraft repair in units of 2^-limit: while the clipped code is over-subscribed, drop one
+     * code of the longest length a level... i.e. take one leaf from the deepest shorter level,
+     * turn it into two leaves one level down, and remove one leaf slot at `limit` (net: same
+     * number of codes, Kraft sum minus one unit). */
+    kraft = 0;
+    for (bits = 1; bits <= limit; bits++) kraft += (unsigned long)bl_count[bits] << (limit - bits);
+    while (kraft > (1ul << limit)) {
         bl_count[limit]--;
-        overflow -= 2;
+        for (bits = limit - 1; bits > 0; bits--) {
+            if (bl_count[bits]) {
+                bl_count[bits]--;
+                bl_count[bits + 1] += 2;
+                break;
+            }
+        }
+        kraft--;
     }
     j = 0;
     for (bits = limit; bits >= 1; bits--)

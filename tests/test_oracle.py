@@ -1,0 +1,155 @@
+"""CPU tests of the oracle (the checker): pinned against the REAL reference's
+token streams (fixtures made from oracle/_ref by tests/golden/make_golden.py,
+and oracle/_ref itself when it is present), against zlib as an independent
+decoder, and against RFC 1951 invariants."""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases, make_input
+
+
+@pytest.fixture(scope="module")
+def O(built):
+    from oracle import pyoracle
+
+    return pyoracle
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c[0])
+def test_oracle_matches_reference_fixture(O, case):
+    name, kind, seed, off, n, ref_toks, last, sha = case
+    data = make_input(kind, seed, off, n)
+    assert hashlib.sha256(data.tobytes()).digest() == sha.tobytes(), "generator drifted from the fixture"
+    ot = O.lz77_segment(data, 0, 0, n, O.params(use_dict=0))
+    assert ot.size == ref_toks.size and np.array_equal(ot, ref_toks)
+    assert O.tokens_expand(ot) == data.tobytes()  # check_lld method
+
+
+def test_oracle_matches_live_reference(O):
+    if not O.have_ref():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        n = int(rng.integers(3, 32769))
+        kind = ["markov", "log", "png", "random"][trial % 4]
+        data = make_input(kind, 100 + trial, int(rng.integers(0, 5000)), n)
+        rt = O.ref_records_to_tokens(O.ref_tokens(data))
+        ot = O.lz77_segment(data, 0, 0, n, O.params(use_dict=0))
+        assert np.array_equal(rt, ot), (kind, n)
+
+
+def test_reference_cost_fields_against_oracle(O):
+    """The reference's own estimate: ll_bits / d_bits of the last record are the optimal
+    unlimited Huffman cost of the token histogram plus one NYT leaf; the oracle's dynamic block for the same
+    tokens must not cost more than that estimate + extra bits + the header estimate by more than a few bits
+    per symbol of length limiting (none at these sizes)."""
+    for case in golden_cases():
+        name, kind, seed, off, n, ref_toks, last, sha = case
+        if n < 3000:
+            continue
+        data = make_input(kind, seed, off, n)
+        body, stats = O.deflate_body(data, 0, n, O.params(use_dict=0, block_mode=3))
+        extra = 0
+        for t in ref_toks:
+            d, l = int(t) >> 16, int(t) & 0xFFFF
+            if d:
+                lt = l - 3
+                extra += 0 if (l == 258 or lt < 8) else (lt.bit_length() - 1) - 2
+                dt = d - 1
+                extra += 0 if dt < 4 else (dt.bit_length() - 1) - 1
+        ref_est = int(last[1]) + int(last[2]) + int(last[3]) + extra + 3
+        # the reference's last record predates its final token's AHT update by design; allow 1% slack
+        assert abs(stats[0].dynamic_bits - ref_est) <= 0.01 * ref_est + 64, (name, stats[0].dynamic_bits, ref_est)
+
+
+@pytest.mark.parametrize("kind,seed", [("markov", 1), ("random", 4), ("log", 3), ("png", 6), ("zeros", 0),
+                                        ("period7", 0)])
+@pytest.mark.parametrize("prm", [dict(), dict(seg_bytes=4096), dict(use_dict=0), dict(window=1024),
+                                 dict(chain_limit=8), dict(block_mode=1), dict(block_mode=2), dict(block_mode=3)],
+                         ids=str)
+def test_stream_roundtrip(O, kind, seed, prm):
+    data = make_input(kind, seed, 0, 100001)
+    z = O.zlib_compress(data, O.params(**prm))
+    assert zlib.decompress(z) == data.tobytes()
+    assert O.zlib_decompress(z, data.size) == data.tobytes()
+
+
+def test_edge_sizes(O):
+    base = make_input("markov", 1, 0, 70000)
+    for n in list(range(0, 12)) + [257, 258, 259, 32767, 32768, 32769, 65535, 65536, 65537]:
+        z = O.zlib_compress(base[:n], O.params())
+        assert zlib.decompress(z) == base[:n].tobytes()
+    assert O.zlib_compress(b"", O.params()) == bytes.fromhex("789c010000ffff00000001")
+
+
+def test_inflate_accepts_zlib_streams(O, built):
+    data = make_input("markov", 2, 0, 300000).tobytes()
+    for lvl in (0, 1, 6, 9):
+        z = zlib.compress(data, lvl)
+        assert O.zlib_decompress(z, len(data)) == data
+        assert built.deflate_decompress(z) == data
+
+
+def test_huffman_lengths_are_valid_and_limited(O):
+    rng = np.random.default_rng(3)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    cases = [rng.integers(0, 1000, 286), rng.integers(0, 3, 286), np.array(fib[:30]), np.array(fib[:19]),
+             np.zeros(30, dtype=np.int64), np.eye(1, 30, 7, dtype=np.int64)[0], np.ones(286, dtype=np.int64)]
+    for freq in cases:
+        for limit in (15, 7):
+            if limit == 7 and freq.size > 19:
+                continue
+            lens = O.huff_lengths(freq, limit)
+            used = lens[lens > 0]
+            assert used.size >= 2 and used.max() <= limit
+            assert sum(2.0 ** -int(l) for l in used) == pytest.approx(1.0)  # complete code
+            assert all(lens[i] > 0 for i in range(freq.size) if freq[i] > 0)
+            # canonical codes are prefix free
+            codes = O.canonical_codes(lens)
+            strs = sorted(format(int(f"{int(c):0{int(l)}b}"[::-1], 2), f"0{int(l)}b") for c, l in zip(codes, lens) if l)
+            assert all(not b.startswith(a) for a, b in zip(strs, strs[1:]))
+
+
+def test_huffman_optimal_when_unconstrained(O):
+    import heapq
+
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        freq = rng.integers(1, 500, int(rng.integers(2, 60)))
+        lens = O.huff_lengths(freq, 15)
+        h = [int(f) for f in freq]
+        heapq.heapify(h)
+        cost = 0
+        while len(h) > 1:
+            a, b = heapq.heappop(h), heapq.heappop(h)
+            cost += a + b
+            heapq.heappush(h, a + b)
+        assert int((freq * lens).sum()) == cost
+
+
+def test_adler_combine(O):
+    data = make_input("png", 6, 0, 200000)
+    cut = 77777
+    a1, a2 = O.adler32(data[:cut]), O.adler32(data[cut:])
+    assert O.adler32_combine(a1, a2, data.size - cut) == zlib.adler32(data.tobytes())
+    from deflate_compression_b200 import shard
+
+    assert shard.adler32_combine(a1, a2, data.size - cut) == zlib.adler32(data.tobytes())
+
+
+def test_dictionary_priming_helps_and_is_consistent(O):
+    data = make_input("log", 3, 0, 200000)
+    z1 = O.zlib_compress(data, O.params(use_dict=1))
+    z0 = O.zlib_compress(data, O.params(use_dict=0))
+    assert len(z1) < len(z0)
+    # a shard body with history equals the same range of the whole stream's segments
+    lo = 3 * 32768
+    body, _ = O.deflate_body(data, lo, data.size, O.params(), is_final=True)
+    whole, stats = O.deflate_body(data, 0, data.size, O.params(), is_final=True)
+    skip = sum(s.out_bytes for s in stats[:3])
+    assert whole[skip:] == body
