@@ -241,11 +241,12 @@ def run_gpu(args) -> None:
             if rank == 0:
                 offs = np.concatenate([[0], np.cumsum(sz)])
                 gather_buf[:sz[0]].copy_(d_out[:sz[0]])
-                reqs = [dist.irecv(gather_buf[int(offs[r]):int(offs[r]) + sz[r]], src=r) for r in range(1, world)]
-                for q in reqs:
+                ops = [dist.P2POp(dist.irecv, gather_buf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
+                for q in dist.batch_isend_irecv(ops):
                     q.wait()
             else:
-                dist.send(d_out[:out_len], dst=0)
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, d_out[:out_len], 0)]):
+                    q.wait()
         return out_len, adler
 
     def sync():

@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(PKG, "libdeflate_b200.so")
+_LIB = os.environ.get("DFL_B200_LIB") or os.path.join(PKG, "libdeflate_b200.so")
 _lib = None
 
 

@@ -41,7 +41,9 @@
 #define NPOS_MAX 65536
 #define HASH_SIZE DFL_HASH_BUCKETS
 #define MATCH_THREADS 1024
-#define REFILL_MIN_IDLE 8
+#ifndef REFILL_MIN_IDLE
+#define REFILL_MIN_IDLE 8 
+#endif
 #define DFL_CHUNK_BYTES (256u << 20)
 #define ADLER_MOD 65521u
 
@@ -157,9 +159,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 /* k_match                                                                   */
 /* ------------------------------------------------------------------------- */
 
-#define MATCH_CHUNK 32   /* positions per speculative parse chunk */
-#define HOP_BATCH 8      /* bucket entries a lane visits before the warp re-converges */
-#define COOP_MIN 64      /* buckets longer than this are walked by the whole warp */
+#ifndef MATCH_CHUNK
+#define MATCH_CHUNK 32 /* positions per speculative parse chunk */
+#endif
+#ifndef HOP_BATCH
+#define HOP_BATCH 8 /* bucket entries a lane visits before the warp re-converges */
+#endif
+#ifndef COOP_MIN
+#define COOP_MIN 64 /* buckets longer than this are walked by the whole warp */
+#endif
 #define SORT_WARPS 32    /* every warp sorts one stripe */
 #define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
 #define SCRATCH_SLOTS 256
