@@ -214,6 +214,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(MatchSmem &S, uint32_t v, in
  * (one stripe, many digits) spread over the banks. */
 __device__ __forceinline__ uint32_t cnt_word(uint32_t stripe, uint32_t d) { return (stripe * SORT_BINS + d) >> 1; }
 __device__ __forceinline__ uint32_t cnt_shift(uint32_t d) { return (d & 1) * 16; }
+#define CNT_WORDS (SORT_BINS * SORT_WARPS / 2) /* 32-bit words of one counter array (8 KB) */
 
 /*
  * Scatter sweep of a sort warp over its stripe, 32 elements per step, 4 steps per
@@ -230,11 +231,13 @@ __device__ __forceinline__ uint32_t cnt_shift(uint32_t d) { return (d & 1) * 16;
  *          cycles of a unit shared by the whole SM).
  */
 template <int PASS, bool FAST>
-__device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k_lo, int k_hi, const uint16_t *gbuf,
+__device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k_lo, int k_hi, int SS, const uint16_t *gbuf,
                                               int lane, int warp)
 {
-    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off);
-    volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(S.off);
+    /* pass-1 cursors at S.off[0..), pass-2 counters / cursors behind them */
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
+    uint32_t *cnt2 = reinterpret_cast<uint32_t *>(S.off) + CNT_WORDS;
+    volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(cnt32);
     const uint32_t lt = lanemask_lt();
     uint32_t eq[4] = {0, 0, 0, 0};
     if (PASS == 2) {
@@ -243,7 +246,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
             if (k_lo + j * 32 + lane < k_hi) eq[j] = __ldcg(gbuf + k_lo + j * 32 + lane);
     }
     for (int k0 = k_lo; k0 < k_hi; k0 += 128) {
-        uint32_t e[4], d[4];
+        uint32_t e[4], d[4], d2[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) { /* bytes + bucket digit of the round's 4 steps: independent work first */
             const int k = k0 + j * 32 + lane;
@@ -251,6 +254,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
             if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
             const uint32_t b = DFL_HASH3(ld4(S.data, soff + (k < k_hi ? e[j] : 0)));
             d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
+            d2[j] = b / SORT_BINS;
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -262,6 +266,8 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
                     const uint32_t sh = cnt_shift(d[j]);
                     const uint32_t slot = (atomicAdd(&cnt32[cnt_word(warp, d[j])], 1u << sh) >> sh) & 0xFFFF;
                     S.list[slot] = (uint16_t)e[j];
+                    /* pass 1 knows where the element lands: count pass 2's digit for that stripe now */
+                    if (PASS == 1) atomicAdd(&cnt2[cnt_word(slot / SS, d2[j])], 1u << cnt_shift(d2[j]));
                 }
             } else {
                 uint32_t peers = __ballot_sync(FULL, valid);
@@ -274,7 +280,9 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
                     const uint32_t ci = warp * SORT_BINS + d[j];
                     const uint32_t base = cnt16[ci];
                     if ((peers >> lane) == 1u) cnt16[ci] = (uint16_t)(base + __popc(peers)); /* top lane of the group */
-                    S.list[base + __popc(peers & lt)] = (uint16_t)e[j];
+                    const uint32_t slot = base + __popc(peers & lt);
+                    S.list[slot] = (uint16_t)e[j];
+                    if (PASS == 1) atomicAdd(&cnt2[cnt_word(slot / SS, d2[j])], 1u << cnt_shift(d2[j]));
                 }
             }
         }
@@ -293,31 +301,30 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
 template <int PASS, bool FAST>
 __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, const uint16_t *gbuf, int tid, int lane, int warp)
 {
-    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off);
-    uint16_t *cnt16 = S.off;
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
+    uint16_t *cnt16 = reinterpret_cast<uint16_t *>(cnt32);
     const int SS = ((NI + SORT_WARPS * 32 - 1) / (SORT_WARPS * 32)) * 32; /* stripe length, multiple of 32 */
 
-    for (int i = tid; i < SORT_BINS * SORT_WARPS / 2; i += MATCH_THREADS) cnt32[i] = 0;
-    __syncthreads();
-    /* count: every thread takes 8 consecutive elements at a time */
-    for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
-        uint32_t ev[4] = {0, 0, 0, 0};
-        if (PASS == 2) {
-            const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(gbuf + k8));
-            ev[0] = v.x; ev[1] = v.y; ev[2] = v.z; ev[3] = v.w;
-        }
-        const uint32_t sw = (uint32_t)(k8 / SS); /* 8 | SS: the 8 elements share a stripe */
+    if (PASS == 1) {
+        for (int i = tid; i < 2 * CNT_WORDS; i += MATCH_THREADS) reinterpret_cast<uint32_t *>(S.off)[i] = 0;
+        __syncthreads();
+        /* count the low digits: every thread takes 8 consecutive positions; their 8 trigrams come
+         * out of three unaligned word reads */
+        for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
+            const uint32_t w0 = ld4(S.data, soff + k8), w1 = ld4(S.data, soff + k8 + 4), w2 = ld4(S.data, soff + k8 + 8);
+            const uint32_t sw = (uint32_t)(k8 / SS); /* 8 | SS: the 8 positions share a stripe */
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (k8 + j < NI) {
-                const uint32_t e = PASS == 1 ? (uint32_t)(k8 + j) : ((ev[j >> 1] >> ((j & 1) * 16)) & 0xFFFF);
-                const uint32_t b = DFL_HASH3(ld4(S.data, soff + e));
-                const uint32_t d = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
-                atomicAdd(&cnt32[cnt_word(sw, d)], 1u << cnt_shift(d));
+            for (int j = 0; j < 8; j++) {
+                if (k8 + j < NI) {
+                    const uint32_t t = j < 4 ? __funnelshift_r(w0, w1, (j & 3) * 8) : __funnelshift_r(w1, w2, (j & 3) * 8);
+                    const uint32_t d = DFL_HASH3(t) & (SORT_BINS - 1);
+                    atomicAdd(&cnt32[cnt_word(sw, d)], 1u << cnt_shift(d));
+                }
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
+    /* (pass 2's digits were counted by pass 1's scatter) */
     /* exclusive scan in (digit, stripe) order: SORT_BINS * SORT_WARPS = 4096 u16 entries, 4 per thread */
     {
         const uint32_t d = tid / (SORT_WARPS / 4), s0 = (tid % (SORT_WARPS / 4)) * 4;
@@ -331,7 +338,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
     __syncthreads();
     {
         const int k_lo = warp * SS, k_hi = (k_lo + SS < NI) ? k_lo + SS : NI;
-        scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, gbuf, lane, warp);
+        scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, SS, gbuf, lane, warp);
     }
     __syncthreads();
 }
@@ -359,13 +366,20 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
     if (NI == 0) {
         for (int i = tid; i < HASH_SIZE + 2; i += MATCH_THREADS) S.off[i] = 0;
     }
-    for (int kk = tid; kk < NI + 1; kk += MATCH_THREADS) {
+    for (int k0 = 0; k0 < NI + 1; k0 += MATCH_THREADS) {
+        const int kk = k0 + tid;
         const int q = kk < NI ? (int)S.list[kk] : 0;
         const int b = kk < NI ? (int)DFL_HASH3(ld4(S.data, soff + q)) : HASH_SIZE;
-        const int pq = kk > 0 ? (int)S.list[kk - 1] : -1;
-        const int pb_ = kk > 0 ? (int)DFL_HASH3(ld4(S.data, soff + pq)) : -1;
-        bad |= kk < NI && ((b < pb_) || (b == pb_ && q <= pq));
-        for (int bb = pb_ + 1; bb <= b; bb++) S.off[bb] = (uint16_t)kk;
+        /* slot kk-1 belongs to the lane below; lane 0 reads it itself */
+        int pq = __shfl_up_sync(FULL, q, 1), pb_ = __shfl_up_sync(FULL, b, 1);
+        if (lane == 0) {
+            pq = kk > 0 && kk <= NI ? (int)S.list[kk - 1] : -1;
+            pb_ = kk > 0 && kk <= NI ? (int)DFL_HASH3(ld4(S.data, soff + pq)) : -1;
+        }
+        if (kk <= NI) {
+            bad |= kk < NI && ((b < pb_) || (b == pb_ && q <= pq));
+            for (int bb = pb_ + 1; bb <= b; bb++) S.off[bb] = (uint16_t)kk;
+        }
     }
     const bool ok = __syncthreads_or(bad) == 0;
     STAMP(7);
@@ -718,9 +732,13 @@ k_parse(long long n, long long seg0, int nseg, dfl_params prm, uint32_t *__restr
 
     int cur = 0, ntok = 0;
     uint32_t extra = 0;
+    /* two windows of candidates kept in flight (tokens are compacted in place, but always behind the reads) */
+    uint32_t v1 = lane < seglen ? tc[lane] : 0, v2 = 32 + lane < seglen ? tc[32 + lane] : 0;
     for (int base = 0; base < seglen; base += 32) {
         int i = base + lane;
-        uint32_t v = i < seglen ? tc[i] : 0;
+        const uint32_t v = v1;
+        v1 = v2;
+        v2 = i + 64 < seglen ? tc[i + 64] : 0;
         int adv = (v >> 16) ? (int)(v & 0xFFFF) : 1;
         int lim = seglen - base < 32 ? seglen - base : 32;
         uint32_t heads = 0;
