@@ -249,3 +249,111 @@ def test_unaligned_device_pointers(D, O):
         ob, _ = O.deflate_body(data, 0, data.size, O.params(), is_final=True)
         assert body == ob
         assert int(d_out[shift_out + out_len:].max()) == 0 and int(d_out[:shift_out].sum()) == 0
+
+
+# --------------------------------------------------------------------------- BASELINE.json configs as parity cases
+# (sizes scaled to what a test run can hold; the properties are size independent)
+
+def _roundtrip_device(D, data: np.ndarray, **prm):
+    """Compress device-resident data, inflate with zlib, compare; returns (stream bytes, compressor)."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    comp = D.Compressor(**prm)
+    d_in = torch.from_numpy(data).to(dev)
+    cap = comp.bound(data.size)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    out_len, adler = comp.deflate_device(d_in.data_ptr(), data.size, 0, True, d_out.data_ptr(), cap)
+    body = d_out[:out_len].cpu().numpy().tobytes()
+    raw = zlib.decompressobj(-15).decompress(body)
+    assert len(raw) == data.size and raw == data.tobytes()
+    assert adler == zlib.adler32(raw)
+    assert comp.sort_fallbacks() == 0
+    return body, comp
+
+
+def test_config3_repetitive_log(D, O):
+    """configs[2]: highly repetitive log data (long matches, deep buckets); 256 MiB here."""
+    data = make_input("log", 3, 0, 256 << 20)
+    body, comp = _roundtrip_device(D, data)
+    assert len(body) < data.size // 20
+    # first / last segments bit-exact against the oracle
+    ob, _ = O.deflate_body(data[: 4 * 32768], 0, 4 * 32768, O.params(), is_final=False)
+    assert body[: len(ob)] == ob
+
+
+def test_config4_incompressible(D, O):
+    """configs[3]: random bytes -> stored blocks, output = input + 10 bytes per 32 KiB segment; 512 MiB here."""
+    import torch
+
+    n = 512 << 20
+    dev = torch.device("cuda:0")
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    assert D.lib().dfl_b200_synth_random(d_in.data_ptr(), n, 4, None) == 0
+    torch.cuda.synchronize()
+    host = d_in.cpu().numpy()
+    assert np.array_equal(host[: 1 << 20], make_input("random", 4, 0, 1 << 20))  # device generator == host generator
+    comp = D.Compressor()
+    cap = comp.bound(n)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    out_len, adler = comp.deflate_device(d_in.data_ptr(), n, 0, True, d_out.data_ptr(), cap)
+    assert out_len == n + 10 * (n // 32768)  # every segment stored: 5 B header + 5 B sync marker
+    body = d_out[:out_len].cpu().numpy()
+    seg = body[: 32778]
+    assert seg[0] == 0 and seg[1] == 0x00 and seg[2] == 0x80 and np.array_equal(seg[5:32773], host[:32768])
+    assert adler == zlib.adler32(host.tobytes())
+    assert zlib.decompressobj(-15).decompress(body.tobytes()) == host.tobytes()
+
+
+def test_config5_mixed_corpus_sharded(D, O):
+    """configs[4]: text + PNG-filtered scanline stripes, sharded over ranks (2 emulated ranks on one GPU),
+    bodies concatenated by rank order inflate to the original; 128 MiB here with 8 MiB stripes."""
+    import torch
+    from deflate_compression_b200 import shard, synth
+
+    n = 128 << 20
+    data = synth.mixed(0, n, stripe=8 << 20)
+    dev = torch.device("cuda:0")
+    d_all = torch.from_numpy(data).to(dev)
+    comp = D.Compressor()
+    bodies, adlers, lens = [], [], []
+    world = 4
+    for r in range(world):
+        lo, hi = shard.shard_range(n, r, world)
+        hist = min(lo, 32768)
+        cap = comp.bound(hi - lo)
+        d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        out_len, adler = comp.deflate_device(d_all.data_ptr() + lo, hi - lo, hist, r == world - 1, d_out.data_ptr(), cap)
+        bodies.append(d_out[:out_len].cpu().numpy().tobytes())
+        adlers.append(adler)
+        lens.append(hi - lo)
+    z = shard.stitch(bodies, adlers, lens)
+    assert zlib.decompress(z) == data.tobytes()
+    # identical to the single-rank stream (segments are independent of the sharding)
+    assert z == comp.compress(data)
+    ratio = n / len(z)
+    assert 1.5 < ratio < 4.0
+
+
+def test_config2_text_256mib(D, O):
+    """configs[1] at full size: 256 MiB Markov text, every block dynamic, round trip, sampled token parity."""
+    n = 256 << 20
+    data = make_input("markov", 2, 0, n)
+    comp = D.Compressor()
+    comp.keep_tokens(True)
+    z = comp.compress(data)
+    assert zlib.decompress(z) == data.tobytes()
+    nseg = comp.num_segments()
+    assert nseg == n // 32768
+    assert all(comp.seg_info(s).btype == 2 for s in range(0, nseg, 97))
+    op = O.params()
+    for s in list(range(0, nseg, 64)) + [nseg - 1]:
+        assert np.array_equal(comp.tokens(s), O.lz77_segment(data, 0, s * 32768, (s + 1) * 32768, op)), s
+    # vs the REAL reference semantics on no-dictionary segments: >= 64 segments
+    comp0 = D.Compressor(use_dict=0)
+    comp0.keep_tokens(True)
+    sub = data[: 64 * 32768]
+    comp0.compress(sub)
+    op0 = O.params(use_dict=0)
+    for s in range(64):
+        assert np.array_equal(comp0.tokens(s), O.lz77_segment(sub, 0, s * 32768, (s + 1) * 32768, op0)), s
