@@ -1342,6 +1342,10 @@ struct dfl_ctx {
     /* host-buffer path */
     uint8_t *d_in, *d_out;
     size_t d_in_cap, d_out_cap;
+    cudaStream_t s_in, s_run, s_out; /* host path: copy-in, kernels, copy-out */
+    cudaEvent_t *e_in, *e_done;
+    unsigned long long *h_totals;     /* pinned: end offset of every piece */
+    int pipe_cap;
     /* bookkeeping */
     long launches;
     long long last_n;
@@ -1490,6 +1494,10 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
+    for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
+    free(ctx->e_in); free(ctx->e_done);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_run); cudaStreamDestroy(ctx->s_out); }
     free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_block_bits); free(ctx->h_out_off);
     for (int i = 0; i < ctx->ev_cap; i++) cudaEventDestroy(ctx->ev[i]);
     free(ctx->ev); free(ctx->ev_class);
@@ -1575,6 +1583,23 @@ static int keep_reserve(dfl_ctx *ctx, size_t n, size_t nseg)
     return DFL_OK;
 }
 
+/* The five kernels of one chunk (segments [s0, s0 + ns) of a stream of nseg segments), on stream st. */
+static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len, int is_final, size_t s0, int ns,
+                        size_t nseg, uint8_t *d_out, size_t out_cap, cudaStream_t st)
+{
+    const dfl_params prm = ctx->prm;
+    LAUNCH(K_MATCH, k_match, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
+           (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
+    LAUNCH(K_PARSE, k_parse, (ns + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st, (long long)n,
+           (long long)s0, ns, prm, ctx->tokcand, ctx->A);
+    LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
+           (long long)s0, ns, prm, ctx->A);
+    LAUNCH(K_SCAN, k_scan, 1, SCAN_THREADS, 0, st, ns, ctx->A, ctx->state);
+    LAUNCH(K_EMIT, k_emit, ns, EMIT_THREADS, 0, st, d_in, (long long)n, (long long)s0, (long long)(nseg - 1),
+           is_final, prm, ctx->tokcand, ctx->A, d_out, (unsigned long long)out_cap, ctx->state);
+    return DFL_OK;
+}
+
 extern "C" int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len,
                                         int is_final, uint8_t *d_out, size_t out_cap, void *stream)
 {
@@ -1606,15 +1631,8 @@ extern "C" int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_
     }
     for (size_t s0 = 0; s0 < nseg; s0 += chunk_segs) {
         int ns = (int)(nseg - s0 < chunk_segs ? nseg - s0 : chunk_segs);
-        LAUNCH(K_MATCH, k_match, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
-               (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
-        LAUNCH(K_PARSE, k_parse, (ns + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st, (long long)n,
-               (long long)s0, ns, prm, ctx->tokcand, ctx->A);
-        LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
-               (long long)s0, ns, prm, ctx->A);
-        LAUNCH(K_SCAN, k_scan, 1, SCAN_THREADS, 0, st, ns, ctx->A, ctx->state);
-        LAUNCH(K_EMIT, k_emit, ns, EMIT_THREADS, 0, st, d_in, (long long)n, (long long)s0, (long long)(nseg - 1),
-               is_final, prm, ctx->tokcand, ctx->A, d_out, (unsigned long long)out_cap, ctx->state);
+        rc = launch_chunk(ctx, d_in, n, hist_len, is_final, s0, ns, nseg, d_out, out_cap, st);
+        if (rc) return rc;
         if (ctx->keep) {
             /* debug / fd_stats path: pull this chunk's tokens and segment records */
             size_t pos0 = s0 * (size_t)prm.seg_bytes;
@@ -1666,12 +1684,40 @@ extern "C" int dfl_b200_deflate_device(dfl_ctx *ctx, const uint8_t *d_in, size_t
     return dfl_b200_deflate_finish(ctx, out_len, adler, stream);
 }
 
+#define HOST_PIPE_BYTES (32u << 20) /* piece size of the host path: H2D, compute and D2H of neighbouring pieces overlap */
+
+static int host_pipe_init(dfl_ctx *ctx, int npieces)
+{
+    if (!ctx->s_in) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    }
+    if (ctx->pipe_cap < npieces) {
+        for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
+        free(ctx->e_in); free(ctx->e_done);
+        if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+        ctx->pipe_cap = 0;
+        ctx->e_in = (cudaEvent_t *)calloc(npieces, sizeof(cudaEvent_t));
+        ctx->e_done = (cudaEvent_t *)calloc(npieces, sizeof(cudaEvent_t));
+        if (!ctx->e_in || !ctx->e_done) return DFL_E_MALLOC;
+        CK(cudaMallocHost(&ctx->h_totals, (size_t)npieces * sizeof(unsigned long long)));
+        for (int i = 0; i < npieces; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->e_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->e_done[i], cudaEventDisableTiming));
+        }
+        ctx->pipe_cap = npieces;
+    }
+    return DFL_OK;
+}
+
 extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                                       size_t *out_len)
 {
     if (!ctx || (!in && n) || !out || !out_len) return DFL_E_INVAL;
     CK(cudaSetDevice(ctx->device));
-    size_t bound = dfl_b200_bound(&ctx->prm, n);
+    const dfl_params prm = ctx->prm;
+    size_t bound = dfl_b200_bound(&prm, n);
     if (ctx->d_in_cap < n + 16) {
         if (ctx->d_in) cudaFree(ctx->d_in);
         ctx->d_in = NULL; ctx->d_in_cap = 0;
@@ -1684,16 +1730,73 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
         CK(cudaMalloc(&ctx->d_out, bound + 16));
         ctx->d_out_cap = bound + 16;
     }
-    cudaStream_t st = 0;
-    if (n) CK(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, st));
+    uint8_t *d_body = ctx->d_out + 2; /* body at +2 so the zlib header can be prepended without a second copy */
     size_t body = 0;
     uint32_t adler = 1;
-    /* body at d_out + 2 so the zlib header can be prepended without a second copy */
-    int rc = dfl_b200_deflate_device(ctx, ctx->d_in, n, 0, 1, ctx->d_out + 2, bound, &body, &adler, st);
-    if (rc) return rc;
-    if (cap < body + 6) return DFL_E_SZ;
-    CK(cudaMemcpyAsync(out + 2, ctx->d_out + 2, body, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const size_t nseg = n ? (n + prm.seg_bytes - 1) / prm.seg_bytes : 0;
+    size_t piece_segs = HOST_PIPE_BYTES / (size_t)prm.seg_bytes;
+    if (piece_segs < 1) piece_segs = 1;
+    const int npieces = (int)((nseg + piece_segs - 1) / piece_segs);
+    if (ctx->keep || npieces < 2) {
+        /* small input, or the token-keeping debug path: one copy in, one call, one copy out */
+        cudaStream_t st = 0;
+        if (n) CK(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, st));
+        int rc = dfl_b200_deflate_device(ctx, ctx->d_in, n, 0, 1, d_body, bound, &body, &adler, st);
+        if (rc) return rc;
+        if (cap < body + 6) return DFL_E_SZ;
+        CK(cudaMemcpyAsync(out + 2, d_body, body, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        /* pipeline over pieces: copy-in of piece i+1, kernels of piece i and copy-out of piece i-1 overlap
+         * on three streams; output offsets stay on the device, each piece's end offset comes back with it */
+        int rc = ensure_ws(ctx, piece_segs);
+        if (rc) return rc;
+        rc = host_pipe_init(ctx, npieces);
+        if (rc) return rc;
+        ctx->ev_n = 0;
+        ctx->nseg_kept = 0;
+        CK(cudaMemsetAsync(ctx->state, 0, sizeof(DevState), ctx->s_run));
+        for (int i = 0; i < npieces; i++) {
+            const size_t lo = (size_t)i * piece_segs * prm.seg_bytes;
+            const size_t hi = (lo + piece_segs * prm.seg_bytes < n) ? lo + piece_segs * prm.seg_bytes : n;
+            CK(cudaMemcpyAsync(ctx->d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_in));
+            CK(cudaEventRecord(ctx->e_in[i], ctx->s_in));
+        }
+        size_t copied = 0;
+        for (int i = 0; i <= npieces; i++) {
+            if (i < npieces) {
+                const size_t s0 = (size_t)i * piece_segs;
+                const int ns = (int)(nseg - s0 < piece_segs ? nseg - s0 : piece_segs);
+                CK(cudaStreamWaitEvent(ctx->s_run, ctx->e_in[i], 0));
+                rc = launch_chunk(ctx, ctx->d_in, n, 0, 1, s0, ns, nseg, d_body, bound, ctx->s_run);
+                if (rc) return rc;
+                if (i == npieces - 1) {
+                    LAUNCH(K_FINAL, k_final, 1, 32, 0, ctx->s_run, (long long)n, ctx->state);
+                    CK(cudaMemcpyAsync(ctx->h_state, ctx->state, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->s_run));
+                }
+                CK(cudaMemcpyAsync(&ctx->h_totals[i], &ctx->state->total_out, sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, ctx->s_run));
+                CK(cudaEventRecord(ctx->e_done[i], ctx->s_run));
+            }
+            if (i >= 1) {
+                /* piece i-1 is complete: its bytes [copied, h_totals[i-1]) can leave while piece i runs */
+                CK(cudaEventSynchronize(ctx->e_done[i - 1]));
+                const size_t end = (size_t)ctx->h_totals[i - 1];
+                if (cap < end + 6) { /* let everything in flight land before the caller's buffers go away */
+                    cudaStreamSynchronize(ctx->s_run);
+                    cudaStreamSynchronize(ctx->s_out);
+                    return DFL_E_SZ;
+                }
+                CK(cudaMemcpyAsync(out + 2 + copied, d_body + copied, end - copied, cudaMemcpyDeviceToHost, ctx->s_out));
+                copied = end;
+            }
+        }
+        CK(cudaStreamSynchronize(ctx->s_out));
+        CK(cudaGetLastError());
+        if (ctx->h_state->error) return DFL_E_SZ;
+        body = (size_t)ctx->h_state->total_out;
+        adler = ctx->h_state->adler;
+    }
     out[0] = 0x78; /* CM = 8, CINFO = 7: header the decoder checks at src/deflate_decompress.c:352-360 */
     out[1] = 0x9C;
     out[2 + body + 0] = (uint8_t)(adler >> 24); /* RFC 1950: Adler-32 MSB first */
