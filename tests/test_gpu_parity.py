@@ -357,3 +357,52 @@ def test_config2_text_256mib(D, O):
     op0 = O.params(use_dict=0)
     for s in range(64):
         assert np.array_equal(comp0.tokens(s), O.lz77_segment(sub, 0, s * 32768, (s + 1) * 32768, op0)), s
+
+
+def test_error_paths(D):
+    """Error behaviour of the C-ABI: small output buffers are reported, never overrun."""
+    import ctypes as C
+
+    import torch
+
+    data = make_input("random", 4, 0, 100000)
+    comp = D.Compressor()
+    out = np.zeros(50000 + 64, dtype=np.uint8)
+    with pytest.raises(D.DflError) as e:
+        comp.compress_into(data.ctypes.data, data.size, out.ctypes.data, 50000)
+    assert e.value.code == -6  # E_SZ
+    assert int(out[50000:].max()) == 0  # nothing past the capacity was touched
+    big = make_input("random", 9, 0, 80 << 20)  # pipelined host path
+    out = np.zeros((40 << 20) + 64, dtype=np.uint8)
+    with pytest.raises(D.DflError) as e:
+        comp.compress_into(big.ctypes.data, big.size, out.ctypes.data, 40 << 20)
+    assert e.value.code == -6
+    assert int(out[40 << 20:].max()) == 0
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(data).to(dev)
+    d_out = torch.zeros(60000, dtype=torch.uint8, device=dev)
+    with pytest.raises(D.DflError) as e:
+        comp.deflate_device(d_in.data_ptr(), data.size, 0, True, d_out.data_ptr(), 40000)
+    assert e.value.code == -6
+    assert int(d_out[40000:].max()) == 0
+    # the context is still usable afterwards
+    z = comp.compress(data)
+    assert zlib.decompress(z) == data.tobytes()
+    L = D.lib()
+    assert L.dfl_b200_compress_host(None, None, 0, None, 0, None) == -11  # E_INVAL
+    ctx = C.c_void_p()
+    assert L.dfl_b200_create(C.byref(ctx), 99, None) == -10  # no such device: E_RANGE
+
+
+def test_context_reuse_and_param_switch(D, O):
+    """One context, many calls of different sizes and parameters (workspace reuse / regrowth)."""
+    comp = D.Compressor()
+    for n in (10, 70000, 3, 33 << 20, 1000, 70 << 20, 40000):
+        data = make_input("markov", 7, 0, n)
+        assert zlib.decompress(comp.compress(data)) == data.tobytes()
+    for prm in (dict(seg_bytes=2048), dict(seg_bytes=32768, window=512), dict(chain_limit=3)):
+        p = D.DflParams(prm.get("window", 32768), prm.get("seg_bytes", 32768), prm.get("chain_limit", 0), 1, 0)
+        assert D.lib().dfl_b200_set_params(comp._ctx, p) == 0
+        comp.params = p
+        data = make_input("log", 3, 0, 200000)
+        assert comp.compress(data) == O.zlib_compress(data, O.params(**prm))
