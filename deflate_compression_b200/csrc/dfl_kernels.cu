@@ -524,30 +524,17 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         } while (0)
 
         for (;;) {
-            /* phase A: find the head's own slot in its bucket (lower bound of p in
-             * list[k, k_hi)), then walk the bucket backwards until a candidate passes
-             * the one-byte filter */
-            if (st == ST_SEEK || st == ST_WALK) {
+            /* phase A: walk the bucket backwards until a candidate passes the 4-byte filter */
+            if (st == ST_WALK) {
 #pragma unroll 1
                 for (int t = 0; t < HOP_BATCH; t++) {
-                    if (st == ST_SEEK) {
-                        if (k < k_hi) {
-                            const int mid = (k + k_hi) >> 1;
-                            if ((int)S.list[mid] < p) k = mid + 1; else k_hi = mid;
-                        } else {
-                            /* k is the slot of p; candidates are k-1 ... k_lo.  A long bucket is
-                             * walked by the whole warp together (phase C) */
-                            st = ST_WALK;
-                        }
-                    } else {
-                        if (k <= k_lo || (K && hops >= K)) { st = ST_DONE; break; }
-                        q = S.list[--k];
-                        if (p - q > W) { st = ST_DONE; break; }
-                        hops++;
-                        /* filter: the 4 bytes ending at offset best_len (the 3 of the trigram while
-                         * nothing is found yet) must match for q to beat the best so far */
-                        if ((ld4(S.data, soff + q + foff) & fmask) == fword) { st = ST_CAND; break; }
-                    }
+                    if (k <= k_lo || (K && hops >= K)) { st = ST_DONE; break; }
+                    q = S.list[--k];
+                    if (p - q > W) { st = ST_DONE; break; }
+                    hops++;
+                    /* filter: the 4 bytes ending at offset best_len (the 3 of the trigram while
+                     * nothing is found yet) must match for q to beat the best so far */
+                    if ((ld4(S.data, soff + q + foff) & fmask) == fword) { st = ST_CAND; break; }
                 }
             }
             /* a long remainder of the bucket is walked by the whole warp together (phase C) */
@@ -587,7 +574,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             /* phase C: finished heads emit their token and move on; idle lanes take new
              * chunks.  One warp reduction per round steers it (votes and shuffles share a
              * slow unit on this chip). */
-            const uint32_t census = __reduce_add_sync(FULL, (st == ST_SEEK || st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) |
+            const uint32_t census = __reduce_add_sync(FULL, (st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) |
                                                                 (st == ST_HEAVY ? 0x10000u : 0u));
             const int n_busy = census & 0xFF, n_fin = (census >> 8) & 0xFF, n_heavy = census >> 16;
             if (n_fin == 32) break;
@@ -674,6 +661,15 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                         const uint32_t bit = 1u << (ci & 31);
                         if (!(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
                     }
+                }
+                /* the new heads find their own slot in their bucket together: lower bound of p in
+                 * list[k, k_hi); candidates are then k-1 ... k_lo */
+                if (st == ST_SEEK) {
+                    while (k < k_hi) {
+                        const int mid = (k + k_hi) >> 1;
+                        if ((int)S.list[mid] < p) k = mid + 1; else k_hi = mid;
+                    }
+                    st = ST_WALK;
                 }
             }
         }
