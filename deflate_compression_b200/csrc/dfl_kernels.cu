@@ -94,6 +94,41 @@ __device__ __forceinline__ uint32_t ld4(const uint32_t *w, uint32_t byte_idx)
     return __funnelshift_r(lo, hi, (byte_idx & 3) * 8);
 }
 
+/* Explicit shared-window addressing for the hot loops: a 32-bit shared address computed once
+ * (ptxas otherwise re-derives the window base with S2R SR_CgaCtaId inside the loops). */
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v)
+{
+    uint32_t o;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+/* unaligned little-endian 4-byte load at shared address a */
+__device__ __forceinline__ uint32_t ld4s(uint32_t a)
+{
+    const uint32_t w = a & ~3u;
+    return __funnelshift_r(lds_u32(w), lds_u32(w + 4), a << 3);
+}
+
 /* RFC 1951 3.2.5: length 3..258 -> symbol 257..285 (same numbers as
  * get_len_code, src/deflate_compress.c:182-200; extra bits per the RFC). */
 __device__ __forceinline__ int len_sym(int len, int &eb, int &ev)
@@ -236,8 +271,11 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
 {
     /* pass-1 cursors at S.off[0..), pass-2 counters / cursors behind them */
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
-    uint32_t *cnt2 = reinterpret_cast<uint32_t *>(S.off) + CNT_WORDS;
     volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(cnt32);
+    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
+    const uint32_t c2base = (uint32_t)__cvta_generic_to_shared(S.off) + CNT_WORDS * 4;
     const uint32_t lt = lanemask_lt();
     uint32_t eq[4] = {0, 0, 0, 0};
     if (PASS == 2) {
@@ -252,7 +290,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
             const int k = k0 + j * 32 + lane;
             e[j] = PASS == 1 ? (uint32_t)k : eq[j];
             if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
-            const uint32_t b = DFL_HASH3(ld4(S.data, soff + (k < k_hi ? e[j] : 0)));
+            const uint32_t b = DFL_HASH3(ld4s(dbase + (k < k_hi ? e[j] : 0)));
             d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
             d2[j] = b / SORT_BINS;
         }
@@ -264,10 +302,10 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
             if (FAST) {
                 if (valid) {
                     const uint32_t sh = cnt_shift(d[j]);
-                    const uint32_t slot = (atomicAdd(&cnt32[cnt_word(warp, d[j])], 1u << sh) >> sh) & 0xFFFF;
-                    S.list[slot] = (uint16_t)e[j];
+                    const uint32_t slot = (atoms_add(cbase + 4 * cnt_word(warp, d[j]), 1u << sh) >> sh) & 0xFFFF;
+                    sts_u16(lbase + 2 * slot, e[j]);
                     /* pass 1 knows where the element lands: count pass 2's digit for that stripe now */
-                    if (PASS == 1) atomicAdd(&cnt2[cnt_word(slot / SS, d2[j])], 1u << cnt_shift(d2[j]));
+                    if (PASS == 1) reds_add(c2base + 4 * cnt_word(slot / SS, d2[j]), 1u << cnt_shift(d2[j]));
                 }
             } else {
                 uint32_t peers = __ballot_sync(FULL, valid);
@@ -281,8 +319,8 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
                     const uint32_t base = cnt16[ci];
                     if ((peers >> lane) == 1u) cnt16[ci] = (uint16_t)(base + __popc(peers)); /* top lane of the group */
                     const uint32_t slot = base + __popc(peers & lt);
-                    S.list[slot] = (uint16_t)e[j];
-                    if (PASS == 1) atomicAdd(&cnt2[cnt_word(slot / SS, d2[j])], 1u << cnt_shift(d2[j]));
+                    sts_u16(lbase + 2 * slot, e[j]);
+                    if (PASS == 1) reds_add(c2base + 4 * cnt_word(slot / SS, d2[j]), 1u << cnt_shift(d2[j]));
                 }
             }
         }
@@ -303,6 +341,8 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
 {
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
     uint16_t *cnt16 = reinterpret_cast<uint16_t *>(cnt32);
+    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
     const int SS = ((NI + SORT_WARPS * 32 - 1) / (SORT_WARPS * 32)) * 32; /* stripe length, multiple of 32 */
 
     if (PASS == 1) {
@@ -311,14 +351,14 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
         /* count the low digits: every thread takes 8 consecutive positions; their 8 trigrams come
          * out of three unaligned word reads */
         for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
-            const uint32_t w0 = ld4(S.data, soff + k8), w1 = ld4(S.data, soff + k8 + 4), w2 = ld4(S.data, soff + k8 + 8);
+            const uint32_t w0 = ld4s(dbase + k8), w1 = ld4s(dbase + k8 + 4), w2 = ld4s(dbase + k8 + 8);
             const uint32_t sw = (uint32_t)(k8 / SS); /* 8 | SS: the 8 positions share a stripe */
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (k8 + j < NI) {
                     const uint32_t t = j < 4 ? __funnelshift_r(w0, w1, (j & 3) * 8) : __funnelshift_r(w1, w2, (j & 3) * 8);
                     const uint32_t d = DFL_HASH3(t) & (SORT_BINS - 1);
-                    atomicAdd(&cnt32[cnt_word(sw, d)], 1u << cnt_shift(d));
+                    reds_add(cbase + 4 * cnt_word(sw, d), 1u << cnt_shift(d));
                 }
             }
         }
@@ -349,6 +389,8 @@ template <bool FAST>
 __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI, uint16_t *gbuf, int tid, int lane, int warp,
                                             DevState *state)
 {
+    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
     long long c0 = clock64(), c1;
 #define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
     sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp);
@@ -368,13 +410,13 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
     }
     for (int k0 = 0; k0 < NI + 1; k0 += MATCH_THREADS) {
         const int kk = k0 + tid;
-        const int q = kk < NI ? (int)S.list[kk] : 0;
-        const int b = kk < NI ? (int)DFL_HASH3(ld4(S.data, soff + q)) : HASH_SIZE;
+        const int q = kk < NI ? (int)lds_u16(lbase + 2 * kk) : 0;
+        const int b = kk < NI ? (int)DFL_HASH3(ld4s(dbase + q)) : HASH_SIZE;
         /* slot kk-1 belongs to the lane below; lane 0 reads it itself */
         int pq = __shfl_up_sync(FULL, q, 1), pb_ = __shfl_up_sync(FULL, b, 1);
         if (lane == 0) {
-            pq = kk > 0 && kk <= NI ? (int)S.list[kk - 1] : -1;
-            pb_ = kk > 0 && kk <= NI ? (int)DFL_HASH3(ld4(S.data, soff + pq)) : -1;
+            pq = kk > 0 && kk <= NI ? (int)lds_u16(lbase + 2 * (kk - 1)) : -1;
+            pb_ = kk > 0 && kk <= NI ? (int)DFL_HASH3(ld4s(dbase + pq)) : -1;
         }
         if (kk <= NI) {
             bad |= kk < NI && ((b < pb_) || (b == pb_ && q <= pq));
@@ -496,6 +538,8 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     {
         enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
         const int W = prm.window, K = prm.chain_limit;
+        const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* shared address of data byte 0 */
+        const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
         const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
         uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
         int st = ST_IDLE;
@@ -513,8 +557,8 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                               \
             else {                                                                      \
                 st = ST_SEEK;                                                           \
-                pw0 = ld4(S.data, soff + p);                                            \
-                pw1 = ld4(S.data, soff + p + 4);                                        \
+                pw0 = ld4s(dbase + p);                                            \
+                pw1 = ld4s(dbase + p + 4);                                        \
                 foff = 0; fmask = 0xFFFFFFu; fword = pw0 & 0xFFFFFFu;                   \
                 const uint32_t b_ = DFL_HASH3(pw0);                                     \
                 k_lo = S.off[b_];                                                       \
@@ -529,12 +573,12 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
 #pragma unroll 1
                 for (int t = 0; t < HOP_BATCH; t++) {
                     if (k <= k_lo || (K && hops >= K)) { st = ST_DONE; break; }
-                    q = S.list[--k];
+                    q = (int)lds_u16(lbase + 2 * (--k));
                     if (p - q > W) { st = ST_DONE; break; }
                     hops++;
                     /* filter: the 4 bytes ending at offset best_len (the 3 of the trigram while
                      * nothing is found yet) must match for q to beat the best so far */
-                    if ((ld4(S.data, soff + q + foff) & fmask) == fword) { st = ST_CAND; break; }
+                    if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
                 }
             }
             /* a long remainder of the bucket is walked by the whole warp together (phase C) */
@@ -546,17 +590,17 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             /* phase B: full compare (check_dup_str) for the lanes holding a candidate */
             if (st == ST_CAND) {
                 int len;
-                uint32_t x = ld4(S.data, soff + q) ^ pw0;
+                uint32_t x = ld4s(dbase + q) ^ pw0;
                 if (x) {
                     len = (__ffs(x) - 1) >> 3;
                 } else {
-                    x = ld4(S.data, soff + q + 4) ^ pw1;
+                    x = ld4s(dbase + q + 4) ^ pw1;
                     if (x) {
                         len = 4 + ((__ffs(x) - 1) >> 3);
                     } else {
                         len = 8;
                         while (len < maxlen) {
-                            x = ld4(S.data, soff + p + len) ^ ld4(S.data, soff + q + len);
+                            x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
                             if (x) { len += (__ffs(x) - 1) >> 3; break; }
                             len += 4;
                         }
@@ -568,7 +612,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     best_len = len;
                     best_dist = p - q;
                     if (len == maxlen) st = ST_DONE;
-                    else { foff = len - 3; fmask = 0xFFFFFFFFu; fword = ld4(S.data, soff + p + foff); }
+                    else { foff = len - 3; fmask = 0xFFFFFFFFu; fword = ld4s(dbase + p + foff); }
                 }
             }
             /* phase C: finished heads emit their token and move on; idle lanes take new
@@ -596,26 +640,26 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
                     int hfoff = hbest == 2 ? 0 : hbest - 3;
                     uint32_t hfmask = hbest == 2 ? 0xFFFFFFu : 0xFFFFFFFFu;
-                    uint32_t hfword = ld4(S.data, soff + hp + hfoff) & hfmask;
+                    uint32_t hfword = ld4s(dbase + hp + hfoff) & hfmask;
                     for (int top = hk; top > hlo; top -= 32) {
                         const int kk = top - 1 - lane;
                         bool valid = kk >= hlo;
-                        const int cq = valid ? (int)S.list[kk] : 0;
+                        const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
                         valid = valid && (hp - cq <= W);
                         uint32_t key = valid ? 0x80000000u : 0u;
-                        if (valid && (ld4(S.data, soff + cq + hfoff) & hfmask) == hfword) {
+                        if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {
                             int len;
-                            uint32_t x = ld4(S.data, soff + cq) ^ hw0;
+                            uint32_t x = ld4s(dbase + cq) ^ hw0;
                             if (x) {
                                 len = (__ffs(x) - 1) >> 3;
                             } else {
-                                x = ld4(S.data, soff + cq + 4) ^ hw1;
+                                x = ld4s(dbase + cq + 4) ^ hw1;
                                 if (x) {
                                     len = 4 + ((__ffs(x) - 1) >> 3);
                                 } else {
                                     len = 8;
                                     while (len < hmax) {
-                                        x = ld4(S.data, soff + hp + len) ^ ld4(S.data, soff + cq + len);
+                                        x = ld4s(dbase + hp + len) ^ ld4s(dbase + cq + len);
                                         if (x) { len += (__ffs(x) - 1) >> 3; break; }
                                         len += 4;
                                     }
@@ -630,7 +674,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                             hbest = (kmax >> 16) & 0x7FFF;
                             hdist = 0xFFFF - (kmax & 0xFFFF);
                             if (hbest == hmax) break;
-                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4(S.data, soff + hp + hfoff);
+                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4s(dbase + hp + hfoff);
                         }
                     }
                     if (lane == L) { best_len = hbest; best_dist = hdist; st = ST_DONE; }
@@ -639,7 +683,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             if (32 - n_busy - n_fin >= REFILL_MIN_IDLE || n_busy == 0) {
                 if (st == ST_DONE) {
                     int adv = 1;
-                    uint32_t t = sd[soff + p];
+                    uint32_t t = lds_u8(dbase + p);
                     if (best_len >= DFL_MIN_MATCH) {
                         t = ((uint32_t)best_dist << 16) | (uint32_t)best_len;
                         adv = best_len;
@@ -667,7 +711,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                 if (st == ST_SEEK) {
                     while (k < k_hi) {
                         const int mid = (k + k_hi) >> 1;
-                        if ((int)S.list[mid] < p) k = mid + 1; else k_hi = mid;
+                        if ((int)lds_u16(lbase + 2 * mid) < p) k = mid + 1; else k_hi = mid;
                     }
                     st = ST_WALK;
                 }
