@@ -221,7 +221,7 @@ class Compressor:
                 for k in range(L.dfl_b200_num_kernels())}
 
     def phase_cycles(self) -> dict:
-        names = ("stage_in", "build", "search", "total", "sort1", "park", "sort2", "offsets", "d8", "d9", "d10", "d11")
+        names = ("stage_in", "build", "search", "total", "sort1", "park", "sort2", "offsets", "s1_count", "s1_scan", "s1_scatter", "d11")
         return {nm: int(lib().dfl_b200_phase_cycles(self._ctx, k)) for k, nm in enumerate(names)}
 
     def sort_fallbacks(self) -> int:

@@ -337,8 +337,11 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
  * atomics), the scatter of a stripe is done in order by its warp.
  */
 template <int PASS, bool FAST>
-__device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, const uint16_t *gbuf, int tid, int lane, int warp)
+__device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, const uint16_t *gbuf, int tid, int lane, int warp,
+                                          DevState *state)
 {
+    long long c0 = clock64(), c1;
+#define STAMP2(slot) do { c1 = clock64(); if (tid == 0 && PASS == 1) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
     uint16_t *cnt16 = reinterpret_cast<uint16_t *>(cnt32);
     const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
@@ -364,6 +367,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
         }
         __syncthreads();
     }
+    STAMP2(8);
     /* (pass 2's digits were counted by pass 1's scatter) */
     /* exclusive scan in (digit, stripe) order: SORT_BINS * SORT_WARPS = 4096 u16 entries, 4 per thread */
     {
@@ -376,11 +380,14 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
         for (int j = 0; j < 4; j++) { cnt16[(s0 + j) * SORT_BINS + d] = (uint16_t)base; base += c[j]; }
     }
     __syncthreads();
+    STAMP2(9);
     {
         const int k_lo = warp * SS, k_hi = (k_lo + SS < NI) ? k_lo + SS : NI;
         scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, SS, gbuf, lane, warp);
     }
     __syncthreads();
+    STAMP2(10);
+#undef STAMP2
 }
 
 /* Sort the NI indexed positions by (bucket, position) into S.list and fill the
@@ -393,13 +400,13 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
     const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
     long long c0 = clock64(), c1;
 #define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
-    sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp);
+    sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp, state);
     STAMP(4);
     /* park the pass-1 order in global scratch: linear, 16 B per thread */
     for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8)
         __stcg(reinterpret_cast<uint4 *>(gbuf + k8), *reinterpret_cast<const uint4 *>(&S.list[k8]));
     STAMP(5);
-    sort_pass<2, FAST>(S, soff, NI, gbuf, tid, lane, warp);
+    sort_pass<2, FAST>(S, soff, NI, gbuf, tid, lane, warp, state);
     STAMP(6);
     /* bucket offsets from the sorted order (off[b] = first slot whose bucket is >= b), and
      * the check that every bucket is in ascending position order.  Slot kk is compared with
@@ -408,19 +415,31 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
     if (NI == 0) {
         for (int i = tid; i < HASH_SIZE + 2; i += MATCH_THREADS) S.off[i] = 0;
     }
-    for (int k0 = 0; k0 < NI + 1; k0 += MATCH_THREADS) {
-        const int kk = k0 + tid;
-        const int q = kk < NI ? (int)lds_u16(lbase + 2 * kk) : 0;
-        const int b = kk < NI ? (int)DFL_HASH3(ld4s(dbase + q)) : HASH_SIZE;
-        /* slot kk-1 belongs to the lane below; lane 0 reads it itself */
-        int pq = __shfl_up_sync(FULL, q, 1), pb_ = __shfl_up_sync(FULL, b, 1);
-        if (lane == 0) {
-            pq = kk > 0 && kk <= NI ? (int)lds_u16(lbase + 2 * (kk - 1)) : -1;
-            pb_ = kk > 0 && kk <= NI ? (int)DFL_HASH3(ld4s(dbase + pq)) : -1;
+    for (int k0 = 0; k0 < NI + 1; k0 += 4 * MATCH_THREADS) {
+        /* 4 consecutive slots per thread (one 8-byte read), the slot before them from the lane below */
+        const int kk0 = k0 + 4 * tid;
+        int q[4], b[4];
+        {
+            uint32_t lo = 0, hi = 0;
+            if (kk0 < NI) asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(lbase + 2 * kk0));
+            q[0] = lo & 0xFFFF; q[1] = lo >> 16; q[2] = hi & 0xFFFF; q[3] = hi >> 16;
         }
-        if (kk <= NI) {
-            bad |= kk < NI && ((b < pb_) || (b == pb_ && q <= pq));
-            for (int bb = pb_ + 1; bb <= b; bb++) S.off[bb] = (uint16_t)kk;
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)DFL_HASH3(ld4s(dbase + q[j])) : HASH_SIZE;
+        int pq = __shfl_up_sync(FULL, q[3], 1), pb_ = __shfl_up_sync(FULL, b[3], 1);
+        if (lane == 0) {
+            pq = kk0 > 0 && kk0 <= NI ? (int)lds_u16(lbase + 2 * (kk0 - 1)) : -1;
+            pb_ = kk0 > 0 && kk0 <= NI ? (int)DFL_HASH3(ld4s(dbase + pq)) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int kk = kk0 + j;
+            if (kk <= NI) {
+                bad |= kk < NI && ((b[j] < pb_) || (b[j] == pb_ && q[j] <= pq));
+                for (int bb = pb_ + 1; bb <= b[j]; bb++) S.off[bb] = (uint16_t)kk;
+            }
+            pq = q[j];
+            pb_ = b[j];
         }
     }
     const bool ok = __syncthreads_or(bad) == 0;
