@@ -272,10 +272,11 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
     /* pass-1 cursors at S.off[0..), pass-2 counters / cursors behind them */
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
     volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(cnt32);
-    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
-    const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
-    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
-    const uint32_t c2base = (uint32_t)__cvta_generic_to_shared(S.off) + CNT_WORDS * 4;
+    uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
+    asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(cbase)); /* keep the window addresses in registers */
+    const uint32_t c2base = cbase + CNT_WORDS * 4; /* only used by pass 1 */
     const uint32_t lt = lanemask_lt();
     uint32_t eq[4] = {0, 0, 0, 0};
     if (PASS == 2) {
@@ -344,8 +345,9 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
 #define STAMP2(slot) do { c1 = clock64(); if (tid == 0 && PASS == 1) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
     uint16_t *cnt16 = reinterpret_cast<uint16_t *>(cnt32);
-    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
-    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
+    uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
+    asm volatile("" : "+r"(dbase), "+r"(cbase));
     const int SS = ((NI + SORT_WARPS * 32 - 1) / (SORT_WARPS * 32)) * 32; /* stripe length, multiple of 32 */
 
     if (PASS == 1) {
@@ -396,8 +398,10 @@ template <bool FAST>
 __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI, uint16_t *gbuf, int tid, int lane, int warp,
                                             DevState *state)
 {
-    const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
-    const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
+    asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
     long long c0 = clock64(), c1;
 #define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
     sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp, state);
@@ -436,7 +440,7 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
             const int kk = kk0 + j;
             if (kk <= NI) {
                 bad |= kk < NI && ((b[j] < pb_) || (b[j] == pb_ && q[j] <= pq));
-                for (int bb = pb_ + 1; bb <= b[j]; bb++) S.off[bb] = (uint16_t)kk;
+                for (int bb = pb_ + 1; bb <= b[j]; bb++) sts_u16(obase + 2 * bb, kk);
             }
             pq = q[j];
             pb_ = b[j];
@@ -557,8 +561,11 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     {
         enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
         const int W = prm.window, K = prm.chain_limit;
-        const uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* shared address of data byte 0 */
-        const uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+        /* shared-window addresses held in registers (the empty asm keeps ptxas from re-deriving them
+         * from special registers inside the loops) */
+        uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* data byte 0 */
+        uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+        asm volatile("" : "+r"(dbase), "+r"(lbase));
         const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
         uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
         int st = ST_IDLE;
