@@ -476,6 +476,7 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
  * evaluated; speculative parses re-synchronise with the true one within a few
  * tokens, so the extra work is small.  k_parse then follows the evaluated heads.
  */
+template <bool HAS_K> /* HAS_K: a chain limit is in force (the hop counters vanish otherwise) */
 __global__ void __launch_bounds__(MATCH_THREADS, 1)
 k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, long long seg0,
         dfl_params prm, uint32_t *__restrict__ tokcand, uint16_t *__restrict__ scratch, DevState *state)
@@ -560,7 +561,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     /* ---- speculative chunk parsers ---- */
     {
         enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
-        const int W = prm.window, K = prm.chain_limit;
+        const int W = prm.window, K = HAS_K ? prm.chain_limit : 0;
         /* shared-window addresses held in registers (the empty asm keeps ptxas from re-deriving them
          * from special registers inside the loops) */
         uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* data byte 0 */
@@ -598,10 +599,10 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             if (st == ST_WALK) {
 #pragma unroll 1
                 for (int t = 0; t < HOP_BATCH; t++) {
-                    if (k <= k_lo || (K && hops >= K)) { st = ST_DONE; break; }
+                    if (k <= k_lo || (HAS_K && hops >= K)) { st = ST_DONE; break; }
                     q = (int)lds_u16(lbase + 2 * (--k));
                     if (p - q > W) { st = ST_DONE; break; }
-                    hops++;
+                    if (HAS_K) hops++;
                     /* filter: the 4 bytes ending at offset best_len (the 3 of the trigram while
                      * nothing is found yet) must match for q to beat the best so far */
                     if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
@@ -610,7 +611,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             /* a long remainder of the bucket is walked by the whole warp together (phase C) */
             if (st == ST_WALK) {
                 int rem = k - k_lo;
-                if (K && K - hops < rem) rem = K - hops;
+                if (HAS_K && K - hops < rem) rem = K - hops;
                 if (rem > COOP_MIN) st = ST_HEAVY;
             }
             /* phase B: full compare (check_dup_str) for the lanes holding a candidate */
@@ -661,8 +662,8 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     int hlo = __shfl_sync(FULL, k_lo, L);
                     const int hmax = __shfl_sync(FULL, maxlen, L);
                     const uint32_t hw0 = __shfl_sync(FULL, pw0, L), hw1 = __shfl_sync(FULL, pw1, L);
-                    const int hhops = __shfl_sync(FULL, hops, L);
-                    if (K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
+                    const int hhops = HAS_K ? __shfl_sync(FULL, hops, L) : 0;
+                    if (HAS_K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
                     int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
                     int hfoff = hbest == 2 ? 0 : hbest - 3;
                     uint32_t hfmask = hbest == 2 ? 0xFFFFFFu : 0xFFFFFFFFu;
@@ -1538,7 +1539,8 @@ extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
         free(ctx);
         return DFL_E_CUDA;
     }
-    if (cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
         cudaMalloc(&ctx->state, sizeof(DevState)) != cudaSuccess ||
         cudaMalloc(&ctx->scratch, (size_t)SCRATCH_SLOTS * NPOS_MAX * sizeof(uint16_t)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_state, sizeof(DevState)) != cudaSuccess) {
@@ -1654,8 +1656,12 @@ static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist
                         size_t nseg, uint8_t *d_out, size_t out_cap, cudaStream_t st)
 {
     const dfl_params prm = ctx->prm;
-    LAUNCH(K_MATCH, k_match, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
-           (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
+    if (prm.chain_limit)
+        LAUNCH(K_MATCH, k_match<true>, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
+               (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
+    else
+        LAUNCH(K_MATCH, k_match<false>, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
+               (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
     LAUNCH(K_PARSE, k_parse, (ns + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st, (long long)n,
            (long long)s0, ns, prm, ctx->tokcand, ctx->A);
     LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
