@@ -56,7 +56,7 @@ struct DevState {
     unsigned long long adl_b;      /* sum of per-segment weighted sums */
     unsigned int error;            /* 1 = output overflow */
     unsigned int adler;            /* final Adler-32 */
-    unsigned long long t_phase[12]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
+    unsigned long long t_phase[24]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
     unsigned int sort_fallbacks;   /* segments whose index had to be rebuilt with the ballot-ranked scatter */
 };
 
@@ -291,7 +291,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
             const int k = k0 + j * 32 + lane;
             e[j] = PASS == 1 ? (uint32_t)k : eq[j];
             if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
-            const uint32_t b = DFL_HASH3(ld4s(dbase + (k < k_hi ? e[j] : 0)));
+            const uint32_t b = DFL_HASH4(ld4s(dbase + (k < k_hi ? e[j] : 0)));
             d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
             d2[j] = b / SORT_BINS;
         }
@@ -362,7 +362,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
             for (int j = 0; j < 8; j++) {
                 if (k8 + j < NI) {
                     const uint32_t t = j < 4 ? __funnelshift_r(w0, w1, (j & 3) * 8) : __funnelshift_r(w1, w2, (j & 3) * 8);
-                    const uint32_t d = DFL_HASH3(t) & (SORT_BINS - 1);
+                    const uint32_t d = DFL_HASH4(t) & (SORT_BINS - 1);
                     reds_add(cbase + 4 * cnt_word(sw, d), 1u << cnt_shift(d));
                 }
             }
@@ -429,11 +429,11 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
             q[0] = lo & 0xFFFF; q[1] = lo >> 16; q[2] = hi & 0xFFFF; q[3] = hi >> 16;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)DFL_HASH3(ld4s(dbase + q[j])) : HASH_SIZE;
+        for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)DFL_HASH4(ld4s(dbase + q[j])) : HASH_SIZE;
         int pq = __shfl_up_sync(FULL, q[3], 1), pb_ = __shfl_up_sync(FULL, b[3], 1);
         if (lane == 0) {
             pq = kk0 > 0 && kk0 <= NI ? (int)lds_u16(lbase + 2 * (kk0 - 1)) : -1;
-            pb_ = kk0 > 0 && kk0 <= NI ? (int)DFL_HASH3(ld4s(dbase + pq)) : -1;
+            pb_ = kk0 > 0 && kk0 <= NI ? (int)DFL_HASH4(ld4s(dbase + pq)) : -1;
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -566,12 +566,13 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
          * from special registers inside the loops) */
         uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* data byte 0 */
         uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
-        asm volatile("" : "+r"(dbase), "+r"(lbase));
+        uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
+        asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
         const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
         uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
         int st = ST_IDLE;
         int i = 0, p = 0, q = 0, k = 0, k_lo = 0, k_hi = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
-        uint32_t pw0 = 0, pw1 = 0, fword = 0, fmask = 0;
+        uint32_t pw0 = 0, pw1 = 0, fword = 0;
         int foff = 0;
 
         /* take position i_ as a parse head (caller has claimed it) */
@@ -581,16 +582,18 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             p = hist + i;                                                               \
             maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;           \
             best_len = 2; best_dist = 0; hops = 0;                                      \
-            if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                               \
-            else {                                                                      \
+            if (maxlen <= DFL_MIN_MATCH) {                                              \
+                st = ST_DONE; /* < 3: literal; == 3: only the nearest-trigram search applies */ \
+                if (maxlen == DFL_MIN_MATCH) pw0 = ld4s(dbase + p);                     \
+            } else {                                                                    \
                 st = ST_SEEK;                                                           \
-                pw0 = ld4s(dbase + p);                                            \
-                pw1 = ld4s(dbase + p + 4);                                        \
-                foff = 0; fmask = 0xFFFFFFu; fword = pw0 & 0xFFFFFFu;                   \
-                const uint32_t b_ = DFL_HASH3(pw0);                                     \
-                k_lo = S.off[b_];                                                       \
+                pw0 = ld4s(dbase + p);                                                  \
+                pw1 = ld4s(dbase + p + 4);                                              \
+                foff = 0; fword = pw0;                                                  \
+                const uint32_t b_ = DFL_HASH4(pw0);                                     \
+                k_lo = (int)lds_u16(obase + 2 * b_);                                    \
                 k = k_lo;                                                               \
-                k_hi = S.off[b_ + 1];                                                   \
+                k_hi = (int)lds_u16(obase + 2 * b_ + 2);                                \
             }                                                                           \
         } while (0)
 
@@ -603,9 +606,10 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     q = (int)lds_u16(lbase + 2 * (--k));
                     if (p - q > W) { st = ST_DONE; break; }
                     if (HAS_K) hops++;
-                    /* filter: the 4 bytes ending at offset best_len (the 3 of the trigram while
-                     * nothing is found yet) must match for q to beat the best so far */
-                    if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
+                    /* filter: the 4 bytes ending at offset best_len (the first 4 while nothing is
+                     * found yet: this walk only looks for matches of >= 4) must match for q to beat
+                     * the best so far */
+                    if (ld4s(dbase + q + foff) == fword) { st = ST_CAND; break; }
                 }
             }
             /* a long remainder of the bucket is walked by the whole warp together (phase C) */
@@ -639,7 +643,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     best_len = len;
                     best_dist = p - q;
                     if (len == maxlen) st = ST_DONE;
-                    else { foff = len - 3; fmask = 0xFFFFFFFFu; fword = ld4s(dbase + p + foff); }
+                    else { foff = len - 3; fword = ld4s(dbase + p + foff); }
                 }
             }
             /* phase C: finished heads emit their token and move on; idle lanes take new
@@ -666,15 +670,14 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     if (HAS_K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
                     int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
                     int hfoff = hbest == 2 ? 0 : hbest - 3;
-                    uint32_t hfmask = hbest == 2 ? 0xFFFFFFu : 0xFFFFFFFFu;
-                    uint32_t hfword = ld4s(dbase + hp + hfoff) & hfmask;
+                    uint32_t hfword = ld4s(dbase + hp + hfoff);
                     for (int top = hk; top > hlo; top -= 32) {
                         const int kk = top - 1 - lane;
                         bool valid = kk >= hlo;
                         const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
                         valid = valid && (hp - cq <= W);
                         uint32_t key = valid ? 0x80000000u : 0u;
-                        if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {
+                        if (valid && ld4s(dbase + cq + hfoff) == hfword) {
                             int len;
                             uint32_t x = ld4s(dbase + cq) ^ hw0;
                             if (x) {
@@ -701,13 +704,36 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                             hbest = (kmax >> 16) & 0x7FFF;
                             hdist = 0xFFFF - (kmax & 0xFFFF);
                             if (hbest == hmax) break;
-                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4s(dbase + hp + hfoff);
+                            hfoff = hbest - 3; hfword = ld4s(dbase + hp + hfoff);
                         }
                     }
                     if (lane == L) { best_len = hbest; best_dist = hdist; st = ST_DONE; }
                 }
             }
             if (32 - n_busy - n_fin >= REFILL_MIN_IDLE || n_busy == 0) {
+                /* Heads whose own bucket held no match of >= 4 bytes: the answer is the NEAREST earlier
+                 * occurrence of the trigram (all remaining matches have length exactly 3, :258 keeps the
+                 * first found), which lives somewhere in the 2^DFL_SUB_BITS buckets of the trigram's group.
+                 * The group is one contiguous range of the list: the warp sweeps it flat, one head at a
+                 * time, and keeps the largest matching position inside the window. */
+                uint32_t need = __ballot_sync(FULL, st == ST_DONE && best_len == 2 && maxlen >= DFL_MIN_MATCH);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int hp = __shfl_sync(FULL, p, L);
+                    const uint32_t hw = __shfl_sync(FULL, pw0, L) & 0xFFFFFFu;
+                    const uint32_t g_ = DFL_HASH4(hw); /* fourth byte 0 -> first bucket of the group */
+                    const int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
+                    uint32_t loc = 0;
+                    for (int kk = ghi - 1 - lane; kk >= glo; kk -= 32) {
+                        const int cq = (int)lds_u16(lbase + 2 * kk);
+                        const int d = hp - cq;
+                        if ((unsigned)(d - 1) < (unsigned)W && (ld4s(dbase + cq) & 0xFFFFFFu) == hw && (uint32_t)cq + 1 > loc)
+                            loc = (uint32_t)cq + 1;
+                    }
+                    loc = __reduce_max_sync(FULL, loc);
+                    if (lane == L && loc) { best_len = DFL_MIN_MATCH; best_dist = p - (int)(loc - 1); }
+                }
                 if (st == ST_DONE) {
                     int adv = 1;
                     uint32_t t = lds_u8(dbase + p);
@@ -1887,7 +1913,7 @@ extern "C" unsigned int dfl_b200_sort_fallbacks(dfl_ctx *ctx) { return ctx ? ctx
 /* k_match SM cycles of the last call, summed over CTAs: 0 stage-in, 1 build, 2 search, 3 total */
 extern "C" unsigned long long dfl_b200_phase_cycles(dfl_ctx *ctx, int k)
 {
-    return (ctx && k >= 0 && k < 12) ? ctx->h_state->t_phase[k] : 0;
+    return (ctx && k >= 0 && k < 24) ? ctx->h_state->t_phase[k] : 0;
 }
 
 extern "C" int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info)

@@ -40,6 +40,15 @@ extern "C" {
 #define DFL_HASH_BUCKETS 15360 /* bucket count (sized to the shared-memory budget); observable only with chain_limit > 0 */
 /* bucket of the 3 bytes packed little-endian in v (low 24 bits): multiplicative hash, range-reduced by mul-hi */
 #define DFL_HASH3(v) ((uint32_t)(((uint64_t)((((uint32_t)(v)) & 0xFFFFFFu) * 0x9E3779B1u) * DFL_HASH_BUCKETS) >> 32))
+/* The index buckets positions by their first FOUR bytes (v = 4 bytes little-endian): the trigram picks a
+ * group of 2^DFL_SUB_BITS neighbouring buckets, the fourth byte one bucket of the group.  Every match of
+ * >= 4 bytes shares the bucket; a 3-byte match is somewhere in the group. */
+#ifndef DFL_SUB_BITS
+#define DFL_SUB_BITS 3
+#endif
+#define DFL_TRI_GROUPS (DFL_HASH_BUCKETS >> DFL_SUB_BITS)
+#define DFL_HASH4(v) (((uint32_t)(((uint64_t)((((uint32_t)(v)) & 0xFFFFFFu) * 0x9E3779B1u) * DFL_TRI_GROUPS) >> 32) << DFL_SUB_BITS) | \
+                      (((((uint32_t)(v)) >> 24) * 0x9E3779B1u) >> (32 - DFL_SUB_BITS)))
 
 /* error codes: 0 ok, negative on error (reference convention: callers test < 0,
  * src/png/png_decoder.c:249).  Values reuse src/include/global_errors.h:24-35. */
@@ -55,7 +64,7 @@ typedef struct dfl_ctx dfl_ctx;
 typedef struct dfl_params {
     int32_t window;      /* 1..32768; reference `sw` */
     int32_t seg_bytes;   /* 1..32768; independent segment (parse restart, one block + sync marker) */
-    int32_t chain_limit; /* 0 = walk the whole chain (reference); K = newest K bucket entries */
+    int32_t chain_limit; /* 0 = walk the whole chain (reference); K = newest K entries of the 4-byte bucket, then the nearest 3-byte match */
     int32_t use_dict;    /* 1 = segments may match into the preceding <= window bytes */
     int32_t block_mode;  /* 0 = cheapest of stored/fixed/dynamic; 1/2/3 force stored/fixed/dynamic */
 } dfl_params;

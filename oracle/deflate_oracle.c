@@ -40,6 +40,16 @@ uint32_t orc_hash3(const uint8_t *p)
     return (uint32_t)(((uint64_t)(v * 0x9E3779B1u) * ORC_HASH_BUCKETS) >> 32);
 }
 
+/* Bucket of the 4 bytes (b3 = the fourth byte, 0 past the end of the segment): the CUDA path's
+ * index (include/deflate_b200.h DFL_HASH4) -- the trigram picks a group of 2^ORC_SUB_BITS
+ * neighbouring buckets, the fourth byte one of them.  Observable only with chain_limit > 0. */
+uint32_t orc_hash4(const uint8_t *p, uint32_t b3)
+{
+    uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    uint32_t grp = (uint32_t)(((uint64_t)(v * 0x9E3779B1u) * (ORC_HASH_BUCKETS >> ORC_SUB_BITS)) >> 32);
+    return (grp << ORC_SUB_BITS) | ((b3 * 0x9E3779B1u) >> (32 - ORC_SUB_BITS));
+}
+
 /* ------------------------------------------------------------------------- */
 /* LZ77: hash-chain longest match + greedy parse                             */
 /* ------------------------------------------------------------------------- */
@@ -75,7 +85,7 @@ long orc_lz77_segment(const uint8_t *buf, long hist_lo, long seg_lo, long seg_hi
     const long W = prm->window;
     const int K = prm->chain_limit;
     long p, ntok = 0, span;
-    int32_t *head, *prev;
+    int32_t *head, *prev, *head4, *prev4;
     long i;
 
     if (!prm->use_dict) hist_lo = seg_lo;
@@ -86,16 +96,25 @@ long orc_lz77_segment(const uint8_t *buf, long hist_lo, long seg_lo, long seg_hi
 
     head = (int32_t *)malloc(sizeof(int32_t) * ORC_HASH_BUCKETS);
     prev = (int32_t *)malloc(sizeof(int32_t) * (size_t)span);
-    if (!head || !prev) { free(head); free(prev); return -1; }
-    for (i = 0; i < ORC_HASH_BUCKETS; i++) head[i] = -1;
+    head4 = (int32_t *)malloc(sizeof(int32_t) * ORC_HASH_BUCKETS);
+    prev4 = (int32_t *)malloc(sizeof(int32_t) * (size_t)span);
+    if (!head || !prev || !head4 || !prev4) { free(head); free(prev); free(head4); free(prev4); return -1; }
+    for (i = 0; i < ORC_HASH_BUCKETS; i++) head[i] = head4[i] = -1;
 
-#define ORC_INSERT(pos)                                              \
-    do {                                                             \
-        if ((pos) + 3 <= seg_hi) {                                   \
-            uint32_t h_ = orc_hash3(buf + (pos));                    \
-            prev[(pos) - hist_lo] = head[h_];                        \
-            head[h_] = (int32_t)((pos) - hist_lo);                   \
-        }                                                            \
+    /* every position with 3 bytes left enters the trigram chain (and, for chain_limit > 0, the
+     * chain of its 4-byte bucket) */
+#define ORC_INSERT(pos)                                                                        \
+    do {                                                                                       \
+        if ((pos) + 3 <= seg_hi) {                                                             \
+            uint32_t h_ = orc_hash3(buf + (pos));                                              \
+            prev[(pos) - hist_lo] = head[h_];                                                  \
+            head[h_] = (int32_t)((pos) - hist_lo);                                             \
+            if (K) {                                                                           \
+                h_ = orc_hash4(buf + (pos), (pos) + 3 < seg_hi ? buf[(pos) + 3] : 0);          \
+                prev4[(pos) - hist_lo] = head4[h_];                                            \
+                head4[h_] = (int32_t)((pos) - hist_lo);                                        \
+            }                                                                                  \
+        }                                                                                      \
     } while (0)
 
     for (p = hist_lo; p < seg_lo; p++) ORC_INSERT(p); /* dictionary priming: indexed, no tokens */
@@ -104,15 +123,13 @@ long orc_lz77_segment(const uint8_t *buf, long hist_lo, long seg_lo, long seg_hi
     while (p < seg_hi) {
         int best_len = 2, best_dist = 0, adv;
         int maxlen = (seg_hi - p) < ORC_MAX_MATCH ? (int)(seg_hi - p) : ORC_MAX_MATCH;
-        if (maxlen >= ORC_MIN_MATCH) {
+        if (maxlen >= ORC_MIN_MATCH && !K) {
+            /* the reference's search: the whole chain */
             int32_t q = head[orc_hash3(buf + p)];
-            int hops = 0;
             while (q >= 0) {
                 long dist = (p - hist_lo) - q;
                 int len;
                 if (dist > W) break;
-                if (K && hops >= K) break;
-                hops++;
                 len = orc_lcp(buf + hist_lo + q, buf + p, maxlen);
                 if (len > best_len) {
                     best_len = len;
@@ -120,6 +137,40 @@ long orc_lz77_segment(const uint8_t *buf, long hist_lo, long seg_lo, long seg_hi
                     if (len == maxlen) break; /* nothing nearer or longer can follow */
                 }
                 q = prev[q];
+            }
+        } else if (maxlen >= ORC_MIN_MATCH) {
+            /* chain_limit K (not in the reference; the semantics are the CUDA path's):
+             * (1) the newest K entries of the 4-byte bucket, looking for matches of >= 4 bytes;
+             * (2) if there is none, the nearest earlier occurrence of the trigram in the window. */
+            if (maxlen > ORC_MIN_MATCH) {
+                int32_t q = head4[orc_hash4(buf + p, buf[p + 3])];
+                int hops = 0;
+                while (q >= 0) {
+                    long dist = (p - hist_lo) - q;
+                    int len;
+                    if (dist > W || hops >= K) break;
+                    hops++;
+                    len = orc_lcp(buf + hist_lo + q, buf + p, maxlen);
+                    if (len > ORC_MIN_MATCH && len > best_len) {
+                        best_len = len;
+                        best_dist = (int)dist;
+                        if (len == maxlen) break;
+                    }
+                    q = prev4[q];
+                }
+            }
+            if (best_len == 2) {
+                int32_t q = head[orc_hash3(buf + p)];
+                while (q >= 0) {
+                    long dist = (p - hist_lo) - q;
+                    if (dist > W) break;
+                    if (orc_lcp(buf + hist_lo + q, buf + p, ORC_MIN_MATCH) == ORC_MIN_MATCH) {
+                        best_len = ORC_MIN_MATCH;
+                        best_dist = (int)dist;
+                        break;
+                    }
+                    q = prev[q];
+                }
             }
         }
         if (best_len < ORC_MIN_MATCH) {
@@ -135,6 +186,8 @@ long orc_lz77_segment(const uint8_t *buf, long hist_lo, long seg_lo, long seg_hi
 #undef ORC_INSERT
     free(head);
     free(prev);
+    free(head4);
+    free(prev4);
     return ntok;
 }
 

@@ -33,6 +33,7 @@ extern "C" {
 #define ORC_NUM_D 30        /* src/include/deflate.h:6 */
 #define ORC_NUM_CL 19
 #define ORC_HASH_BUCKETS 15360 /* bucket hash range; only observable when chain_limit > 0 */
+#define ORC_SUB_BITS 3          /* buckets per trigram group = 2^3 (include/deflate_b200.h DFL_SUB_BITS) */
 
 /* Token encoding shared with the CUDA path: literal -> byte value (dist field 0);
  * match -> (dist << 16) | len, len 3..258, dist 1..32768. */
@@ -42,7 +43,7 @@ extern "C" {
 typedef struct orc_params {
     int32_t window;      /* sliding window (reference arg `sw`), 1..32768 */
     int32_t seg_bytes;   /* independent segment size; parse restarts, one block + sync marker each */
-    int32_t chain_limit; /* 0 = unlimited (reference behaviour); K = newest K bucket entries */
+    int32_t chain_limit; /* 0 = unlimited (reference behaviour); K = newest K entries of the 4-byte bucket, then the nearest 3-byte match */
     int32_t use_dict;    /* 1: a segment may match into the <=window bytes before it */
     int32_t block_mode;  /* 0 = choose cheapest of stored/fixed/dynamic; 1/2/3 = force stored/fixed/dynamic */
 } orc_params;
@@ -57,6 +58,7 @@ typedef struct orc_seg_stats {
 
 void orc_default_params(orc_params *p);
 uint32_t orc_hash3(const uint8_t *p);
+uint32_t orc_hash4(const uint8_t *p, uint32_t b3);
 
 /* Greedy LZ77 parse of buf[seg_lo, seg_hi) with history buf[hist_lo, seg_lo).
  * Writes at most (seg_hi - seg_lo) tokens; returns the token count. */
