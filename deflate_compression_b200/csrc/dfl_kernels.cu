@@ -129,6 +129,14 @@ __device__ __forceinline__ uint32_t ld4s(uint32_t a)
     return __funnelshift_r(lds_u32(w), lds_u32(w + 4), a << 3);
 }
 
+/* DFL_HASH4 with the group width chosen at run time: sb = 0 gives plain trigram buckets (DFL_HASH3),
+ * sb = DFL_SUB_BITS the 4-byte buckets.  ngrp = DFL_HASH_BUCKETS >> sb. */
+__device__ __forceinline__ uint32_t hash4(uint32_t v, uint32_t ngrp, int sb)
+{
+    const uint32_t grp = __umulhi((v & 0xFFFFFFu) * 0x9E3779B1u, ngrp);
+    return (grp << sb) | __funnelshift_l((v >> 24) * 0x9E3779B1u, 0u, sb);
+}
+
 /* RFC 1951 3.2.5: length 3..258 -> symbol 257..285 (same numbers as
  * get_len_code, src/deflate_compress.c:182-200; extra bits per the RFC). */
 __device__ __forceinline__ int len_sym(int len, int &eb, int &ev)
@@ -203,6 +211,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 #ifndef COOP_MIN
 #define COOP_MIN 64 /* buckets longer than this are walked by the whole warp */
 #endif
+#ifndef SPLIT_MIN_SQ
+#define SPLIT_MIN_SQ 3u /* split the trigram buckets when the sampled sum of squares exceeds this many times the sample count */
+#endif
 #define SORT_WARPS 32    /* every warp sorts one stripe */
 #define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
 #define SCRATCH_SLOTS 256
@@ -267,8 +278,9 @@ __device__ __forceinline__ uint32_t cnt_shift(uint32_t d) { return (d & 1) * 16;
  */
 template <int PASS, bool FAST>
 __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k_lo, int k_hi, int SS, const uint16_t *gbuf,
-                                              int lane, int warp)
+                                              int lane, int warp, int sb)
 {
+    const uint32_t ngrp = HASH_SIZE >> sb;
     /* pass-1 cursors at S.off[0..), pass-2 counters / cursors behind them */
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
     volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(cnt32);
@@ -291,7 +303,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
             const int k = k0 + j * 32 + lane;
             e[j] = PASS == 1 ? (uint32_t)k : eq[j];
             if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
-            const uint32_t b = DFL_HASH4(ld4s(dbase + (k < k_hi ? e[j] : 0)));
+            const uint32_t b = hash4(ld4s(dbase + (k < k_hi ? e[j] : 0)), ngrp, sb);
             d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
             d2[j] = b / SORT_BINS;
         }
@@ -339,8 +351,9 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
  */
 template <int PASS, bool FAST>
 __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, const uint16_t *gbuf, int tid, int lane, int warp,
-                                          DevState *state)
+                                          DevState *state, int sb)
 {
+    const uint32_t ngrp = HASH_SIZE >> sb;
     long long c0 = clock64(), c1;
 #define STAMP2(slot) do { c1 = clock64(); if (tid == 0 && PASS == 1) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
@@ -362,7 +375,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
             for (int j = 0; j < 8; j++) {
                 if (k8 + j < NI) {
                     const uint32_t t = j < 4 ? __funnelshift_r(w0, w1, (j & 3) * 8) : __funnelshift_r(w1, w2, (j & 3) * 8);
-                    const uint32_t d = DFL_HASH4(t) & (SORT_BINS - 1);
+                    const uint32_t d = hash4(t, ngrp, sb) & (SORT_BINS - 1);
                     reds_add(cbase + 4 * cnt_word(sw, d), 1u << cnt_shift(d));
                 }
             }
@@ -385,7 +398,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
     STAMP2(9);
     {
         const int k_lo = warp * SS, k_hi = (k_lo + SS < NI) ? k_lo + SS : NI;
-        scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, SS, gbuf, lane, warp);
+        scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, SS, gbuf, lane, warp, sb);
     }
     __syncthreads();
     STAMP2(10);
@@ -396,21 +409,22 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
  * bucket offsets.  Returns (to every thread) whether the order verified. */
 template <bool FAST>
 __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI, uint16_t *gbuf, int tid, int lane, int warp,
-                                            DevState *state)
+                                            DevState *state, int sb)
 {
+    const uint32_t ngrp = HASH_SIZE >> sb;
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
     uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
     uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
     asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
     long long c0 = clock64(), c1;
 #define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
-    sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp, state);
+    sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp, state, sb);
     STAMP(4);
     /* park the pass-1 order in global scratch: linear, 16 B per thread */
     for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8)
         __stcg(reinterpret_cast<uint4 *>(gbuf + k8), *reinterpret_cast<const uint4 *>(&S.list[k8]));
     STAMP(5);
-    sort_pass<2, FAST>(S, soff, NI, gbuf, tid, lane, warp, state);
+    sort_pass<2, FAST>(S, soff, NI, gbuf, tid, lane, warp, state, sb);
     STAMP(6);
     /* bucket offsets from the sorted order (off[b] = first slot whose bucket is >= b), and
      * the check that every bucket is in ascending position order.  Slot kk is compared with
@@ -429,11 +443,11 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
             q[0] = lo & 0xFFFF; q[1] = lo >> 16; q[2] = hi & 0xFFFF; q[3] = hi >> 16;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)DFL_HASH4(ld4s(dbase + q[j])) : HASH_SIZE;
+        for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)hash4(ld4s(dbase + q[j]), ngrp, sb) : HASH_SIZE;
         int pq = __shfl_up_sync(FULL, q[3], 1), pb_ = __shfl_up_sync(FULL, b[3], 1);
         if (lane == 0) {
             pq = kk0 > 0 && kk0 <= NI ? (int)lds_u16(lbase + 2 * (kk0 - 1)) : -1;
-            pb_ = kk0 > 0 && kk0 <= NI ? (int)DFL_HASH4(ld4s(dbase + pq)) : -1;
+            pb_ = kk0 > 0 && kk0 <= NI ? (int)hash4(ld4s(dbase + pq), ngrp, sb) : -1;
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -546,14 +560,46 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
 
     /* ---- index: positions with 3 bytes available, sorted by (bucket, position) ---- */
     const int NI = npos >= 3 ? npos - 2 : 0;
+    /* Bucket width.  Splitting the trigram buckets by the fourth byte pays when the trigram buckets are
+     * long (text, images, logs).  On data with hardly any repetition (ciphertext, compressed payloads)
+     * nearly every head ends in the nearest-trigram sweep over a whole group, and plain trigram buckets
+     * -- searched in a single pass -- are cheaper.  Decided per segment from a 1-in-8 sample of the
+     * positions: sum of squared trigram-bucket counts / samples = 1 + (candidates a position would see) / 8.
+     * The token stream does not depend on it (every chain is walked to the end either way); with a chain
+     * limit the buckets are always split so that the limit means one thing. */
+    int sb = DFL_SUB_BITS;
+    if (!HAS_K) {
+        uint32_t *off32 = reinterpret_cast<uint32_t *>(S.off);
+        uint32_t obase_ = (uint32_t)__cvta_generic_to_shared(S.off), dbase_ = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+        for (int i2 = tid; i2 < (HASH_SIZE + 2) / 2; i2 += MATCH_THREADS) off32[i2] = 0;
+        __syncthreads();
+        for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
+            const uint32_t b = DFL_HASH3(ld4s(dbase_ + k8));
+            reds_add(obase_ + 4 * (b >> 1), 1u << ((b & 1) * 16));
+        }
+        __syncthreads();
+        uint32_t sq = 0;
+        for (int i2 = tid; i2 < HASH_SIZE / 2; i2 += MATCH_THREADS) {
+            const uint32_t w = off32[i2], lo_ = w & 0xFFFF, hi_ = w >> 16;
+            sq += lo_ * lo_ + hi_ * hi_;
+        }
+        sq = __reduce_add_sync(FULL, sq);
+        if (lane == 0) S.scan_w[warp] = sq;
+        __syncthreads();
+        sq = __reduce_add_sync(FULL, S.scan_w[lane]);
+        __syncthreads();
+        const uint32_t nsamp = (uint32_t)(NI + 7) / 8;
+        if (sq <= SPLIT_MIN_SQ * nsamp) sb = 0;
+        if (tid == 0 && sb == 0) atomicAdd(&state->t_phase[20], 1ull); /* segments indexed by plain trigram buckets */
+    }
     {
         unsigned int smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         uint16_t *gbuf = scratch + (size_t)(smid % SCRATCH_SLOTS) * NPOS_MAX; /* one CTA per SM: private slot */
-        if (!build_index<true>(S, soff, NI, gbuf, tid, lane, warp, state)) {
+        if (!build_index<true>(S, soff, NI, gbuf, tid, lane, warp, state, sb)) {
             /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
             if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-            build_index<false>(S, soff, NI, gbuf, tid, lane, warp, state);
+            build_index<false>(S, soff, NI, gbuf, tid, lane, warp, state, sb);
         }
     }
     const long long t2 = clock64();
@@ -562,6 +608,10 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     {
         enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
         const int W = prm.window, K = HAS_K ? prm.chain_limit : 0;
+        const uint32_t ngrp = HASH_SIZE >> sb;
+        /* first filter of a walk: 4 bytes when the buckets are split (the walk only looks for matches
+         * of >= 4, the trigram sweep does the rest), the trigram otherwise */
+        const uint32_t fmask0 = sb ? 0xFFFFFFFFu : 0xFFFFFFu;
         /* shared-window addresses held in registers (the empty asm keeps ptxas from re-deriving them
          * from special registers inside the loops) */
         uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* data byte 0 */
@@ -572,7 +622,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
         int st = ST_IDLE;
         int i = 0, p = 0, q = 0, k = 0, k_lo = 0, k_hi = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
-        uint32_t pw0 = 0, pw1 = 0, fword = 0;
+        uint32_t pw0 = 0, pw1 = 0, fword = 0, fmask = 0;
         int foff = 0;
 
         /* take position i_ as a parse head (caller has claimed it) */
@@ -582,18 +632,19 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             p = hist + i;                                                               \
             maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;           \
             best_len = 2; best_dist = 0; hops = 0;                                      \
-            if (maxlen <= DFL_MIN_MATCH) {                                              \
-                st = ST_DONE; /* < 3: literal; == 3: only the nearest-trigram search applies */ \
-                if (maxlen == DFL_MIN_MATCH) pw0 = ld4s(dbase + p);                     \
-            } else {                                                                    \
-                st = ST_SEEK;                                                           \
+            if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                               \
+            else {                                                                      \
                 pw0 = ld4s(dbase + p);                                                  \
-                pw1 = ld4s(dbase + p + 4);                                              \
-                foff = 0; fword = pw0;                                                  \
-                const uint32_t b_ = DFL_HASH4(pw0);                                     \
-                k_lo = (int)lds_u16(obase + 2 * b_);                                    \
-                k = k_lo;                                                               \
-                k_hi = (int)lds_u16(obase + 2 * b_ + 2);                                \
+                if (sb && maxlen == DFL_MIN_MATCH) { st = ST_DONE; } /* split buckets: only the trigram sweep applies */ \
+                else {                                                                  \
+                    st = ST_SEEK;                                                       \
+                    pw1 = ld4s(dbase + p + 4);                                          \
+                    foff = 0; fmask = fmask0; fword = pw0 & fmask0;                     \
+                    const uint32_t b_ = hash4(pw0, ngrp, sb);                           \
+                    k_lo = (int)lds_u16(obase + 2 * b_);                                \
+                    k = k_lo;                                                           \
+                    k_hi = (int)lds_u16(obase + 2 * b_ + 2);                            \
+                }                                                                       \
             }                                                                           \
         } while (0)
 
@@ -606,10 +657,9 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     q = (int)lds_u16(lbase + 2 * (--k));
                     if (p - q > W) { st = ST_DONE; break; }
                     if (HAS_K) hops++;
-                    /* filter: the 4 bytes ending at offset best_len (the first 4 while nothing is
-                     * found yet: this walk only looks for matches of >= 4) must match for q to beat
-                     * the best so far */
-                    if (ld4s(dbase + q + foff) == fword) { st = ST_CAND; break; }
+                    /* filter: the 4 bytes ending at offset best_len (fmask0 while nothing is found
+                     * yet) must match for q to beat the best so far */
+                    if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
                 }
             }
             /* a long remainder of the bucket is walked by the whole warp together (phase C) */
@@ -643,7 +693,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     best_len = len;
                     best_dist = p - q;
                     if (len == maxlen) st = ST_DONE;
-                    else { foff = len - 3; fword = ld4s(dbase + p + foff); }
+                    else { foff = len - 3; fmask = 0xFFFFFFFFu; fword = ld4s(dbase + p + foff); }
                 }
             }
             /* phase C: finished heads emit their token and move on; idle lanes take new
@@ -670,14 +720,15 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     if (HAS_K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
                     int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
                     int hfoff = hbest == 2 ? 0 : hbest - 3;
-                    uint32_t hfword = ld4s(dbase + hp + hfoff);
+                    uint32_t hfmask = hbest == 2 ? fmask0 : 0xFFFFFFFFu;
+                    uint32_t hfword = ld4s(dbase + hp + hfoff) & hfmask;
                     for (int top = hk; top > hlo; top -= 32) {
                         const int kk = top - 1 - lane;
                         bool valid = kk >= hlo;
                         const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
                         valid = valid && (hp - cq <= W);
                         uint32_t key = valid ? 0x80000000u : 0u;
-                        if (valid && ld4s(dbase + cq + hfoff) == hfword) {
+                        if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {
                             int len;
                             uint32_t x = ld4s(dbase + cq) ^ hw0;
                             if (x) {
@@ -704,7 +755,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                             hbest = (kmax >> 16) & 0x7FFF;
                             hdist = 0xFFFF - (kmax & 0xFFFF);
                             if (hbest == hmax) break;
-                            hfoff = hbest - 3; hfword = ld4s(dbase + hp + hfoff);
+                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4s(dbase + hp + hfoff);
                         }
                     }
                     if (lane == L) { best_len = hbest; best_dist = hdist; st = ST_DONE; }
@@ -716,13 +767,13 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                  * first found), which lives somewhere in the 2^DFL_SUB_BITS buckets of the trigram's group.
                  * The group is one contiguous range of the list: the warp sweeps it flat, one head at a
                  * time, and keeps the largest matching position inside the window. */
-                uint32_t need = __ballot_sync(FULL, st == ST_DONE && best_len == 2 && maxlen >= DFL_MIN_MATCH);
+                uint32_t need = sb ? __ballot_sync(FULL, st == ST_DONE && best_len == 2 && maxlen >= DFL_MIN_MATCH) : 0u;
                 while (need) {
                     const int L = __ffs(need) - 1;
                     need &= need - 1;
                     const int hp = __shfl_sync(FULL, p, L);
                     const uint32_t hw = __shfl_sync(FULL, pw0, L) & 0xFFFFFFu;
-                    const uint32_t g_ = DFL_HASH4(hw); /* fourth byte 0 -> first bucket of the group */
+                    const uint32_t g_ = hash4(hw, ngrp, sb); /* fourth byte 0 -> first bucket of the group */
                     const int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
                     uint32_t loc = 0;
                     for (int kk = ghi - 1 - lane; kk >= glo; kk -= 32) {
