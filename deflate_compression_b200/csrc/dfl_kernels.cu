@@ -214,6 +214,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 #ifndef SPLIT_MIN_SQ
 #define SPLIT_MIN_SQ 3u /* split the trigram buckets when the sampled sum of squares exceeds this many times the sample count */
 #endif
+#ifndef SEARCH_WARPS
+#define SEARCH_WARPS 32  /* warps that run the chunk parsers (the index build uses all 32) */
+#endif
+#ifndef SKIP_OVERRUN
+#define SKIP_OVERRUN 1   /* a chunk some chain has already entered is not started on its own */
+#endif
 #define SORT_WARPS 32    /* every warp sorts one stripe */
 #define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
 #define SCRATCH_SLOTS 256
@@ -604,8 +610,12 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     }
     const long long t2 = clock64();
 
-    /* ---- speculative chunk parsers ---- */
-    {
+    /* ---- speculative chunk parsers ----
+     * Run by the first SEARCH_WARPS warps only: chains die as they merge, so with one chunk per lane
+     * half the lanes of a warp sit idle behind its slowest chain; fewer lanes that each take several
+     * chunks from the shared counter keep the warps' lanes occupied (the SM is issue bound: what counts
+     * is useful lanes per instruction, not resident warps). */
+    if (warp < SEARCH_WARPS) {
         enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
         const int W = prm.window, K = HAS_K ? prm.chain_limit : 0;
         const uint32_t ngrp = HASH_SIZE >> sb;
@@ -807,7 +817,10 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     } else {
                         const int ci = c * MATCH_CHUNK;
                         const uint32_t bit = 1u << (ci & 31);
-                        if (!(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
+                        /* a chain that has already claimed a head inside this chunk covers it (it runs until
+                         * it meets a claimed head); starting here too would only add speculative heads */
+                        const bool entered = SKIP_OVERRUN && MATCH_CHUNK == 32 && S.claimed[ci >> 5] != 0;
+                        if (!entered && !(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
                     }
                 }
                 /* the new heads find their own slot in their bucket together: lower bound of p in
