@@ -286,6 +286,7 @@ template <int PASS, bool FAST>
 __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k_lo, int k_hi, int SS, const uint16_t *gbuf,
                                               int lane, int warp, int sb)
 {
+    const uint32_t ss_inv = SS ? 0xFFFFFFFFu / (uint32_t)SS + 1u : 0u; /* x / SS == umulhi(x, ss_inv) for x * SS < 2^32 */
     const uint32_t ngrp = HASH_SIZE >> sb;
     /* pass-1 cursors at S.off[0..), pass-2 counters / cursors behind them */
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
@@ -324,7 +325,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
                     const uint32_t slot = (atoms_add(cbase + 4 * cnt_word(warp, d[j]), 1u << sh) >> sh) & 0xFFFF;
                     sts_u16(lbase + 2 * slot, e[j]);
                     /* pass 1 knows where the element lands: count pass 2's digit for that stripe now */
-                    if (PASS == 1) reds_add(c2base + 4 * cnt_word(slot / SS, d2[j]), 1u << cnt_shift(d2[j]));
+                    if (PASS == 1) reds_add(c2base + 4 * cnt_word(__umulhi(slot, ss_inv), d2[j]), 1u << cnt_shift(d2[j]));
                 }
             } else {
                 uint32_t peers = __ballot_sync(FULL, valid);
@@ -339,7 +340,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
                     if ((peers >> lane) == 1u) cnt16[ci] = (uint16_t)(base + __popc(peers)); /* top lane of the group */
                     const uint32_t slot = base + __popc(peers & lt);
                     sts_u16(lbase + 2 * slot, e[j]);
-                    if (PASS == 1) reds_add(c2base + 4 * cnt_word(slot / SS, d2[j]), 1u << cnt_shift(d2[j]));
+                    if (PASS == 1) reds_add(c2base + 4 * cnt_word(__umulhi(slot, ss_inv), d2[j]), 1u << cnt_shift(d2[j]));
                 }
             }
         }
@@ -368,6 +369,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
     uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
     asm volatile("" : "+r"(dbase), "+r"(cbase));
     const int SS = ((NI + SORT_WARPS * 32 - 1) / (SORT_WARPS * 32)) * 32; /* stripe length, multiple of 32 */
+    const uint32_t ss_inv = SS ? 0xFFFFFFFFu / (uint32_t)SS + 1u : 0u;     /* x / SS == umulhi(x, ss_inv) for x * SS < 2^32 */
 
     if (PASS == 1) {
         for (int i = tid; i < 2 * CNT_WORDS; i += MATCH_THREADS) reinterpret_cast<uint32_t *>(S.off)[i] = 0;
@@ -376,7 +378,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
          * out of three unaligned word reads */
         for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
             const uint32_t w0 = ld4s(dbase + k8), w1 = ld4s(dbase + k8 + 4), w2 = ld4s(dbase + k8 + 8);
-            const uint32_t sw = (uint32_t)(k8 / SS); /* 8 | SS: the 8 positions share a stripe */
+            const uint32_t sw = __umulhi((uint32_t)k8, ss_inv); /* 8 | SS: the 8 positions share a stripe */
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (k8 + j < NI) {
@@ -438,7 +440,12 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
     bool bad = false;
     if (NI == 0) {
         for (int i = tid; i < HASH_SIZE + 2; i += MATCH_THREADS) S.off[i] = 0;
+        return true;
     }
+    /* every offset starts as "unset"; the first slot of each non-empty bucket writes its own; the
+     * empty buckets then take the offset of the next non-empty one (suffix minimum) */
+    for (int i = tid; i < (HASH_SIZE + 2) / 2; i += MATCH_THREADS) reinterpret_cast<uint32_t *>(S.off)[i] = 0xFFFFFFFFu;
+    __syncthreads();
     for (int k0 = 0; k0 < NI + 1; k0 += 4 * MATCH_THREADS) {
         /* 4 consecutive slots per thread (one 8-byte read), the slot before them from the lane below */
         const int kk0 = k0 + 4 * tid;
@@ -460,11 +467,42 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
             const int kk = kk0 + j;
             if (kk <= NI) {
                 bad |= kk < NI && ((b[j] < pb_) || (b[j] == pb_ && q[j] <= pq));
-                for (int bb = pb_ + 1; bb <= b[j]; bb++) sts_u16(obase + 2 * bb, kk);
+                if (b[j] != pb_) sts_u16(obase + 2 * b[j], kk); /* slot NI carries bucket HASH_SIZE: the end marker */
             }
             pq = q[j];
             pb_ = b[j];
         }
+    }
+    __syncthreads();
+    {
+        /* suffix minimum over the HASH_SIZE + 1 offsets: 16 consecutive entries per thread */
+        const int e0 = tid * 16;
+        uint32_t v[16], m = 0xFFFFu;
+#pragma unroll
+        for (int j = 15; j >= 0; j--) {
+            v[j] = e0 + j <= HASH_SIZE ? lds_u16(obase + 2 * (e0 + j)) : 0xFFFFu;
+            m = v[j] < m ? v[j] : m;
+        }
+        /* minimum over all threads to the right: inclusive suffix scan in the warp, then across warps */
+        uint32_t x = m;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_down_sync(FULL, x, o);
+            if (lane + o < 32 && y < x) x = y;
+        }
+        uint32_t carry = __shfl_down_sync(FULL, x, 1);
+        if (lane == 31) carry = 0xFFFFu;
+        if (lane == 0) S.scan_w[warp] = x;
+        __syncthreads();
+        for (int w = warp + 1; w < MATCH_THREADS / 32; w++) {
+            const uint32_t y = S.scan_w[w];
+            carry = y < carry ? y : carry;
+        }
+#pragma unroll
+        for (int j = 15; j >= 0; j--) {
+            carry = v[j] < carry ? v[j] : carry;
+            if (e0 + j <= HASH_SIZE && v[j] == 0xFFFFu) sts_u16(obase + 2 * (e0 + j), carry);
+        }
+        if (tid == 0) S.off[HASH_SIZE + 1] = (uint16_t)NI;
     }
     const bool ok = __syncthreads_or(bad) == 0;
     STAMP(7);
