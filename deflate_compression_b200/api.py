@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         L.dfl_b200_deflate_finish.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), vp]
         L.dfl_b200_compress_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dfl_b200_keep_tokens.argtypes = [vp, C.c_int]
+        L.dfl_b200_set_parse_mode.argtypes = [vp, C.c_int]
         L.dfl_b200_num_segments.restype = C.c_long
         L.dfl_b200_num_segments.argtypes = [vp]
         L.dfl_b200_seg_info.argtypes = [vp, C.c_long, C.POINTER(DflSegInfo)]
@@ -192,6 +193,12 @@ class Compressor:
     # ---- parity / stats ----
     def keep_tokens(self, enable: bool = True) -> None:
         lib().dfl_b200_keep_tokens(self._ctx, int(enable))
+
+    def set_parse_mode(self, mode: int) -> None:
+        """0 = by segment count, 1 = warp per segment, 2 = CTA per segment (same tokens)."""
+        rc = lib().dfl_b200_set_parse_mode(self._ctx, int(mode))
+        if rc:
+            raise DflError(rc, "dfl_b200_set_parse_mode")
 
     def num_segments(self) -> int:
         return int(lib().dfl_b200_num_segments(self._ctx))

@@ -121,6 +121,10 @@ long dfl_b200_num_segments(dfl_ctx *ctx);
 int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info);
 long dfl_b200_tokens(dfl_ctx *ctx, long seg, uint32_t *tokens, long cap);
 
+/* Which kernel resolves the greedy parse of a chunk: 0 = chosen by the chunk's segment count (default),
+ * 1 = one warp per segment (k_parse_warp), 2 = one CTA per segment (k_parse).  Same tokens either way. */
+int dfl_b200_set_parse_mode(dfl_ctx *ctx, int mode);
+
 /* Number of kernels this context has launched (bench.py's gpu_launches). */
 long dfl_b200_kernel_launches(dfl_ctx *ctx);
 /* Device milliseconds of each kernel class over the last deflate call

@@ -406,3 +406,22 @@ def test_context_reuse_and_param_switch(D, O):
         comp.params = p
         data = make_input("log", 3, 0, 200000)
         assert comp.compress(data) == O.zlib_compress(data, O.params(**prm))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("kind,seed,n", [("markov", 11, 300001), ("random", 12, 100000), ("log", 13, 200000),
+                                         ("zeros", 0, 70000), ("markov", 14, 5)])
+def test_parse_kernels_agree(D, O, mode, kind, seed, n):
+    """k_parse (CTA per segment, pointer doubling) and k_parse_warp (warp per segment) resolve the
+    same greedy parse: tokens == oracle's with either one forced."""
+    data = make_input(kind, seed, 0, n)
+    comp = D.Compressor()
+    comp.set_parse_mode(mode)
+    comp.keep_tokens(True)
+    z = comp.compress(data)
+    op = O.params()
+    for s in range(comp.num_segments()):
+        lo, hi = s * 32768, min(n, (s + 1) * 32768)
+        assert np.array_equal(comp.tokens(s), O.lz77_segment(data, 0, lo, hi, op)), f"mode {mode} segment {s}"
+    assert z == O.zlib_compress(data, op)
+    comp.close()
