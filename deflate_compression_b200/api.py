@@ -84,6 +84,13 @@ def lib() -> C.CDLL:
         L.dfl_b200_compress_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dfl_b200_keep_tokens.argtypes = [vp, C.c_int]
         L.dfl_b200_set_parse_mode.argtypes = [vp, C.c_int]
+        L.dfl_b200_seg_index.restype = C.c_long
+        L.dfl_b200_seg_index.argtypes = [vp, vp, C.c_long]
+        L.dfl_b200_seg_index_device.restype = vp
+        L.dfl_b200_seg_index_device.argtypes = [vp]
+        L.dfl_b200_inflate_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, C.c_size_t, vp, C.c_size_t,
+                                              C.POINTER(C.c_uint32), vp]
+        L.dfl_b200_decompress_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp, C.c_size_t]
         L.dfl_b200_num_segments.restype = C.c_long
         L.dfl_b200_num_segments.argtypes = [vp]
         L.dfl_b200_seg_info.argtypes = [vp, C.c_long, C.POINTER(DflSegInfo)]
@@ -193,6 +200,42 @@ class Compressor:
     # ---- parity / stats ----
     def keep_tokens(self, enable: bool = True) -> None:
         lib().dfl_b200_keep_tokens(self._ctx, int(enable))
+
+    # ---- segment index + GPU inflate ----
+    def seg_index(self) -> np.ndarray:
+        """Byte offset of every segment of the last compress call in the DEFLATE body, + the body length."""
+        cnt = int(lib().dfl_b200_seg_index(self._ctx, None, 0))
+        if cnt < 0:
+            raise DflError(cnt, "dfl_b200_seg_index")
+        off = np.zeros(cnt, dtype=np.uint64)
+        rc = int(lib().dfl_b200_seg_index(self._ctx, off.ctypes.data, cnt))
+        if rc < 0:
+            raise DflError(rc, "dfl_b200_seg_index")
+        return off
+
+    def seg_index_device(self) -> int:
+        return int(lib().dfl_b200_seg_index_device(self._ctx) or 0)
+
+    def inflate_device(self, d_body: int, body_len: int, d_seg_off: int, nseg: int, d_out: int, n: int,
+                       hist_len: int = 0, stream: int = 0) -> int:
+        """Segment-parallel inflate of a body this library wrote; returns the Adler-32 of the n bytes."""
+        adler = C.c_uint32(0)
+        rc = lib().dfl_b200_inflate_device(self._ctx, d_body, body_len, d_seg_off, nseg, self.params.seg_bytes, hist_len,
+                                           d_out, n, C.byref(adler), stream)
+        if rc:
+            raise DflError(rc, "dfl_b200_inflate_device")
+        return int(adler.value)
+
+    def decompress(self, z: bytes, seg_off: np.ndarray, n: int) -> bytes:
+        """zlib stream + its segment index -> the n original bytes, inflated on the GPU (host buffers)."""
+        src = np.frombuffer(z, dtype=np.uint8)
+        off = np.ascontiguousarray(seg_off, dtype=np.uint64)
+        out = np.empty(max(n, 1), dtype=np.uint8)
+        rc = lib().dfl_b200_decompress_host(self._ctx, src.ctypes.data, src.size, off.ctypes.data, off.size - 1,
+                                            self.params.seg_bytes, out.ctypes.data, n)
+        if rc:
+            raise DflError(rc, "dfl_b200_decompress_host")
+        return out[:n].tobytes()
 
     def set_parse_mode(self, mode: int) -> None:
         """0 = by segment count, 1 = warp per segment, 2 = CTA per segment (same tokens)."""

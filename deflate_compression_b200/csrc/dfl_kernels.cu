@@ -47,8 +47,8 @@
 #define DFL_CHUNK_BYTES (256u << 20)
 #define ADLER_MOD 65521u
 
-enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_NUM };
-static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final"};
+enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_INFLATE, K_NUM };
+static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final", "k_inflate"};
 
 struct DevState {
     unsigned long long total_out;  /* bytes of deflate body written so far */
@@ -1642,6 +1642,378 @@ __global__ void k_synth_random(uint8_t *out, unsigned long long n, unsigned long
 }
 
 /* ------------------------------------------------------------------------- */
+/* k_inflate                                                                 */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Segment-parallel inflate of a stream this library produced (the CPU
+ * twin is host/deflate_decompress.c, the reference's is src/deflate_decompress.c:146-409).  Every
+ * segment starts byte aligned at a known offset (the segment index k_scan computed), so one warp
+ * decodes one segment: lane 0 runs the Huffman decoder (RFC 1951 3.2.3-3.2.7: stored, fixed and
+ * dynamic blocks), literals are stored as they come, a match is copied by the whole warp.  A match
+ * may reach into the output of earlier segments (dictionary priming on the compress side); those
+ * bytes are written by other warps, so every warp publishes how much of its segment is complete
+ * (release) and a reader waits for the bytes it needs (acquire).  Segments are handed out in the
+ * order warps start (a ticket), so a warp only ever waits for warps that are already running.
+ */
+#define INF_WARPS 4
+#define INF_LL_BITS 10
+#define INF_D_BITS 8
+#define INF_PUBLISH 1024 /* bytes between progress updates */
+
+struct InfTables {
+    uint16_t ll[1 << INF_LL_BITS]; /* (symbol << 4) | length, 0 = longer than INF_LL_BITS */
+    uint16_t ds[1 << INF_D_BITS];
+    uint16_t sorted[288 + 32];     /* symbols ordered by (length, symbol): lit/len then distance */
+    uint16_t count[2][16], first[2][16], offs[2][16]; /* canonical decode per code length */
+    uint8_t lens[288 + 32];
+    uint8_t cl[128];               /* code-length code: (symbol << 3) | length */
+};
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+/* LSB-first bit reader over the (4-byte aligned view of the) body; lane 0 only */
+struct BitReader {
+    const uint32_t *words;
+    unsigned long long nwords, wi;
+    unsigned long long buf;
+    int cnt;
+    __device__ __forceinline__ uint32_t ldw(unsigned long long i) const { return i < nwords ? __ldg(words + i) : 0u; }
+    __device__ __forceinline__ void init(unsigned long long byte_pos)
+    {
+        wi = byte_pos >> 2;
+        const int sh = (int)(byte_pos & 3) * 8;
+        buf = (unsigned long long)(ldw(wi++) >> sh);
+        cnt = 32 - sh;
+        refill();
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (cnt <= 32) { buf |= (unsigned long long)ldw(wi++) << cnt; cnt += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek(int nb) const { return (uint32_t)buf & ((1u << nb) - 1u); }
+    __device__ __forceinline__ void skip(int nb) { buf >>= nb; cnt -= nb; }
+    __device__ __forceinline__ uint32_t get(int nb) { const uint32_t v = peek(nb); skip(nb); return v; }
+    __device__ __forceinline__ unsigned long long byte_pos() const { return (wi * 32 - (unsigned long long)cnt) >> 3; }
+};
+
+/* canonical decode, one bit at a time (codes longer than the table): returns symbol or -1 */
+__device__ __forceinline__ int inf_slow(BitReader &br, const InfTables &T, int which)
+{
+    int code = 0, index_off = 0;
+    for (int len = 1; len <= 15; len++) {
+        code |= (int)((br.buf >> (len - 1)) & 1);
+        const int cnt = T.count[which][len], first = T.first[which][len];
+        if (code - first < cnt && code >= first) {
+            br.skip(len);
+            return T.sorted[(which ? 288 : 0) + T.offs[which][len] + (code - first)];
+        }
+        code <<= 1;
+        (void)index_off;
+    }
+    return -1;
+}
+
+/* Build the decode structures of one alphabet from T.lens[base .. base + n) (executed by the whole warp).
+ * Returns false if the lengths oversubscribe the code space. */
+__device__ bool inf_build(InfTables &T, int which, int base, int n, int lane)
+{
+    uint16_t *tab = which ? T.ds : T.ll;
+    const int bits = which ? INF_D_BITS : INF_LL_BITS;
+    for (int i = lane; i < (1 << bits); i += 32) tab[i] = 0;
+    if (lane < 16) T.count[which][lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        for (int s = 0; s < n; s++) T.count[which][T.lens[base + s]]++;
+        T.count[which][0] = 0;
+        int code = 0, off = 0, left = 1;
+        bool ok = true;
+        for (int len = 1; len <= 15; len++) {
+            left <<= 1;
+            left -= T.count[which][len];
+            if (left < 0) ok = false;
+            code = (code + T.count[which][len - 1]) << 1;
+            T.first[which][len] = (uint16_t)code;
+            T.offs[which][len] = (uint16_t)off;
+            off += T.count[which][len];
+        }
+        T.first[which][0] = ok ? 1 : 0;
+        /* symbols in (length, symbol) order; next[] reuses first[] + running counters kept in registers */
+        int nxt[16];
+#pragma unroll
+        for (int len = 0; len < 16; len++) nxt[len] = T.offs[which][len];
+        for (int s = 0; s < n; s++) {
+            const int l = T.lens[base + s];
+            if (l) {
+                int slot = 0;
+#pragma unroll
+                for (int len = 1; len < 16; len++)
+                    if (len == l) slot = nxt[len]++;
+                T.sorted[(which ? 288 : 0) + slot] = (uint16_t)s;
+            }
+        }
+    }
+    __syncwarp();
+    const bool ok = T.first[which][0] != 0;
+    /* table: every code of <= bits bits, replicated over the unused high index bits */
+    int total = 0;
+    for (int len = 1; len <= 15; len++) total += T.count[which][len];
+    for (int r = lane; r < total; r += 32) {
+        const int s = T.sorted[(which ? 288 : 0) + r];
+        const int l = T.lens[base + s];
+        if (l <= bits) {
+            const int code = T.first[which][l] + (r - T.offs[which][l]);
+            const uint32_t rev = __brev((uint32_t)code) >> (32 - l);
+            for (uint32_t i = rev; i < (1u << bits); i += 1u << l) tab[i] = (uint16_t)((s << 4) | l);
+        }
+    }
+    __syncwarp();
+    return ok;
+}
+
+__global__ void __launch_bounds__(INF_WARPS * 32)
+k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const unsigned long long *__restrict__ seg_off,
+          long long nseg, int seg_bytes, long long n, long long hist_len, uint8_t *d_out, unsigned int *progress,
+          unsigned int *ticket, DevState *state)
+{
+    __shared__ InfTables s_tab[INF_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    InfTables &T = s_tab[warp];
+    long long s = 0;
+    if (lane == 0) s = (long long)atomicAdd(ticket, 1u);
+    s = __shfl_sync(FULL, s, 0);
+    if (s >= nseg) return;
+    const long long seg_lo = s * seg_bytes;
+    const int seglen = (int)(((seg_lo + seg_bytes < n) ? seg_lo + seg_bytes : n) - seg_lo);
+    uint8_t *out = d_out + seg_lo;
+    const unsigned long long a0 = (unsigned long long)((uintptr_t)body & 3);
+    BitReader br;
+    br.words = reinterpret_cast<const uint32_t *>(body - a0);
+    br.nwords = (body_len + a0 + 3) >> 2;
+    const unsigned long long seg_end = seg_off[s + 1] + a0;
+    if (lane == 0) br.init(seg_off[s] + a0);
+    int pos = 0, pub = 0;
+    int err = 0;
+
+    for (;;) {
+        /* ---- block header ---- */
+        int hdr = 0;
+        if (lane == 0) {
+            br.refill();
+            hdr = (int)br.get(3);
+        }
+        hdr = __shfl_sync(FULL, hdr, 0);
+        const int bfinal = hdr & 1, btype = hdr >> 1;
+        if (btype == 0) {
+            /* stored: LEN, NLEN at the next byte boundary, then LEN raw bytes */
+            unsigned long long src = 0;
+            int len = 0;
+            if (lane == 0) {
+                br.skip(br.cnt & 7);
+                br.refill();
+                const uint32_t l = br.get(16);
+                br.refill();
+                const uint32_t nl = br.get(16);
+                if ((l ^ nl) != 0xFFFFu) err = 1;
+                len = (int)l;
+                src = br.byte_pos();
+            }
+            len = __shfl_sync(FULL, len, 0);
+            src = __shfl_sync(FULL, src, 0);
+            err = __shfl_sync(FULL, err, 0);
+            if (err || pos + len > seglen) { err = 1; break; }
+            const uint8_t *sb = reinterpret_cast<const uint8_t *>(br.words) + src;
+            for (int t = lane; t < len; t += 32) out[pos + t] = __ldg(sb + t);
+            pos += len;
+            __syncwarp();
+            if (lane == 0) br.init(src + (unsigned long long)len);
+        } else if (btype == 1 || btype == 2) {
+            int nll = 288, nd = 30;
+            if (btype == 1) {
+                for (int i = lane; i < 288; i += 32) T.lens[i] = (uint8_t)fixed_ll_len(i);
+                T.lens[288 + lane] = 5;
+                nd = 32;
+            } else {
+                /* dynamic: HLIT, HDIST, HCLEN, the code-length code, then the run-length coded lengths */
+                if (lane == 0) {
+                    br.refill();
+                    nll = (int)br.get(5) + 257;
+                    nd = (int)br.get(5) + 1;
+                    const int ncl = (int)br.get(4) + 4;
+                    uint8_t cl_len[19];
+#pragma unroll
+                    for (int i = 0; i < 19; i++) cl_len[i] = 0;
+                    for (int i = 0; i < ncl; i++) {
+                        br.refill();
+                        const int v = (int)br.get(3);
+#pragma unroll
+                        for (int j = 0; j < 19; j++)
+                            if (j == c_cl_order[i]) cl_len[j] = (uint8_t)v;
+                    }
+                    /* canonical code of the 19 symbols -> 7-bit table */
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nxt[8];
+#pragma unroll
+                    for (int j = 0; j < 19; j++) {
+#pragma unroll
+                        for (int l = 1; l < 8; l++)
+                            if (cl_len[j] == l) cnt[l]++;
+                    }
+                    int code = 0;
+                    nxt[0] = 0;
+#pragma unroll
+                    for (int l = 1; l < 8; l++) { code = (code + (l > 1 ? cnt[l - 1] : 0)) << 1; nxt[l] = code; }
+                    for (int i = 0; i < 128; i++) T.cl[i] = 0;
+#pragma unroll
+                    for (int j = 0; j < 19; j++) {
+                        const int l = cl_len[j];
+                        if (l) {
+                            int c = 0;
+#pragma unroll
+                            for (int q = 1; q < 8; q++)
+                                if (q == l) c = nxt[q]++;
+                            const uint32_t rev = __brev((uint32_t)c) >> (32 - l);
+                            for (uint32_t i = rev; i < 128u; i += 1u << l) T.cl[i] = (uint8_t)((j << 3) | l);
+                        }
+                    }
+                    if (nll > 286 || nd > 30) err = 1;
+                    int i = 0, prev = 0;
+                    while (!err && i < nll + nd) {
+                        br.refill();
+                        const uint32_t e = T.cl[br.peek(7)];
+                        if (!e) { err = 1; break; }
+                        br.skip((int)(e & 7));
+                        const int sym = (int)(e >> 3);
+                        int rep = 1, val = sym;
+                        if (sym == 16) { rep = 3 + (int)br.get(2); val = prev; if (i == 0) err = 1; }
+                        else if (sym == 17) { rep = 3 + (int)br.get(3); val = 0; }
+                        else if (sym == 18) { rep = 11 + (int)br.get(7); val = 0; }
+                        if (i + rep > nll + nd) { err = 1; break; }
+                        for (int r = 0; r < rep; r++, i++) T.lens[i < nll ? i : 288 + (i - nll)] = (uint8_t)val;
+                        prev = val;
+                    }
+                    for (int k = nll; k < 288; k++) T.lens[k] = 0;
+                    for (int k = nd; k < 32; k++) T.lens[288 + k] = 0;
+                }
+                err = __shfl_sync(FULL, err, 0);
+                if (err) break;
+                nll = 288; nd = 32; /* the unused tails were zeroed */
+            }
+            __syncwarp();
+            const bool ok1 = inf_build(T, 0, 0, nll, lane);
+            const bool ok2 = inf_build(T, 1, 288, nd, lane);
+            if (!ok1 || !ok2) { err = 1; break; }
+            /* ---- tokens ---- */
+            for (;;) {
+                int mlen = 0, mdist = 0, npos = pos;
+                if (lane == 0) {
+                    for (;;) {
+                        br.refill();
+                        int sym;
+                        const uint32_t e = T.ll[br.peek(INF_LL_BITS)];
+                        if (e) { br.skip((int)(e & 15)); sym = (int)(e >> 4); }
+                        else sym = inf_slow(br, T, 0);
+                        if (sym < 0) { mlen = -2; break; }
+                        if (sym < 256) {
+                            if (npos >= seglen) { mlen = -2; break; }
+                            out[npos++] = (uint8_t)sym;
+                            if (npos - pos >= INF_PUBLISH) break; /* mlen = 0: literals only, lets the warp publish progress */
+                            continue;
+                        }
+                        if (sym == 256) { mlen = -1; break; }
+                        if (sym > 285) { mlen = -2; break; }
+                        mlen = c_len_base[sym - 257] + (int)br.get(c_len_extra[sym - 257]);
+                        br.refill();
+                        int ds;
+                        const uint32_t e2 = T.ds[br.peek(INF_D_BITS)];
+                        if (e2) { br.skip((int)(e2 & 15)); ds = (int)(e2 >> 4); }
+                        else ds = inf_slow(br, T, 1);
+                        if (ds < 0 || ds > 29) { mlen = -2; break; }
+                        mdist = c_dist_base[ds] + (int)br.get(c_dist_extra[ds]);
+                        break;
+                    }
+                    /* bytes of earlier segments this match reads must be complete */
+                    if (mlen > 0) {
+                        const long long g_src = seg_lo + npos - mdist;
+                        if (g_src < -hist_len) mlen = -2; /* reaches before the history the caller supplied */
+                        if (mlen > 0 && g_src < seg_lo) {
+                            long long need_hi = g_src + mlen < seg_lo ? g_src + mlen : seg_lo; /* exclusive */
+                            for (long long k = (g_src < 0 ? 0 : g_src / seg_bytes); k < s && k * seg_bytes < need_hi; k++) {
+                                const long long klo = k * seg_bytes;
+                                const unsigned int want = (unsigned int)((need_hi - klo < seg_bytes) ? need_hi - klo : seg_bytes);
+                                unsigned int got;
+                                do {
+                                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(progress + k) : "memory");
+                                    if (got < want && *(volatile unsigned int *)&state->error) { got = 0xFFFFFFFFu; mlen = -2; }
+                                } while (got < want);
+                            }
+                        }
+                    }
+                }
+                mlen = __shfl_sync(FULL, mlen, 0);
+                mdist = __shfl_sync(FULL, mdist, 0);
+                pos = __shfl_sync(FULL, npos, 0);
+                if (mlen == -1) break;                 /* end of block */
+                if (mlen < 0 || pos + mlen > seglen) { err = 1; break; }
+                __syncwarp(); /* lane 0's literals are ordered before the copy's reads */
+                /* copy: source bytes repeat with period mdist when the match overlaps itself */
+                if (mlen > 0) {
+                    const uint8_t *srcp = out + pos - mdist;
+                    for (int t = lane; t < mlen; t += 32) {
+                        const int so = mdist >= mlen ? t : t % mdist;
+                        out[pos + t] = __ldcg(srcp + so);
+                    }
+                }
+                pos += mlen;
+                __syncwarp();
+                if (lane == 0 && pos - pub >= INF_PUBLISH) {
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + s), "r"((unsigned int)pos) : "memory");
+                    pub = pos;
+                }
+            }
+            if (err) break;
+        } else {
+            err = 1;
+            break;
+        }
+        unsigned long long bp = 0;
+        if (lane == 0) bp = br.byte_pos();
+        bp = __shfl_sync(FULL, bp, 0);
+        if (bfinal || bp >= seg_end) break;
+    }
+    if (!err && pos != seglen) err = 1;
+    if (err && lane == 0) atomicExch(&state->error, 2u);
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + s), "r"(err ? 0xFFFFFFFFu : (unsigned int)seglen) : "memory");
+    }
+    /* Adler-32 partial sums of the segment (same bookkeeping as k_match) */
+    if (!err) {
+        uint32_t a = 0;
+        unsigned long long b = 0;
+        for (int i = lane; i < seglen; i += 32) {
+            const uint32_t v = __ldcg(out + i);
+            a += v;
+            b += (unsigned long long)v * (uint32_t)(seglen - i);
+        }
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(FULL, a, o);
+            b += __shfl_xor_sync(FULL, b, o);
+        }
+        if (lane == 0) {
+            const unsigned long long am = a % ADLER_MOD;
+            const unsigned long long rest = (unsigned long long)(n - (seg_lo + seglen)) % ADLER_MOD;
+            atomicAdd(&state->adl_a, am);
+            atomicAdd(&state->adl_b, (b % ADLER_MOD + am * rest) % ADLER_MOD);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* host side: context + C-ABI                                                */
 /* ------------------------------------------------------------------------- */
 
@@ -1665,6 +2037,11 @@ struct dfl_ctx {
     unsigned long long *h_totals;     /* pinned: end offset of every piece */
     int pipe_cap;
     int parse_mode; /* 0 = by segment count, 1 = k_parse_warp, 2 = k_parse */
+    /* segment index of the last compress call (byte offset of every segment in the body, + the end) and inflate state */
+    unsigned long long *seg_index;
+    size_t seg_index_cap, seg_index_n;
+    unsigned int *inf_progress;
+    size_t inf_cap;
     /* bookkeeping */
     long launches;
     long long last_n;
@@ -1713,6 +2090,7 @@ extern "C" const char *dfl_b200_strerror(int err)
     case DFL_E_RANGE: return "E_RANGE: parameter out of range";
     case DFL_E_INVAL: return "E_INVAL: invalid argument";
     case DFL_E_CUDA: return "CUDA failure (no sm_100 device, driver error or kernel fault)";
+    case DFL_E_DATA: return "E_ZINV: corrupt stream, wrong segment index or Adler-32 mismatch";
     default: return "unknown error";
     }
 }
@@ -1744,6 +2122,19 @@ static void free_ws(dfl_ctx *ctx)
     ctx->tokcand = NULL;
     ctx->seg_blob = NULL;
     ctx->ws_segs = 0;
+}
+
+static int ensure_index(dfl_ctx *ctx, size_t nseg)
+{
+    if (ctx->seg_index_cap < nseg + 1) {
+        if (ctx->seg_index) cudaFree(ctx->seg_index);
+        ctx->seg_index = NULL;
+        ctx->seg_index_cap = 0;
+        CK(cudaMalloc(&ctx->seg_index, (nseg + 1) * sizeof(unsigned long long)));
+        ctx->seg_index_cap = nseg + 1;
+    }
+    ctx->seg_index_n = nseg;
+    return DFL_OK;
 }
 
 static int ensure_ws(dfl_ctx *ctx, size_t nseg_chunk)
@@ -1818,6 +2209,8 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
+    if (ctx->seg_index) cudaFree(ctx->seg_index);
+    if (ctx->inf_progress) cudaFree(ctx->inf_progress);
     for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
     free(ctx->e_in); free(ctx->e_done);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -1937,6 +2330,9 @@ static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist
     LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
            (long long)s0, ns, prm, ctx->A);
     LAUNCH(K_SCAN, k_scan, 1, SCAN_THREADS, 0, st, ns, ctx->A, ctx->state);
+    /* segment index: where each segment starts in the body, and (entry nseg) where the body ends so far */
+    CK(cudaMemcpyAsync(ctx->seg_index + s0, ctx->A.out_off, (size_t)ns * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(ctx->seg_index + s0 + ns, &ctx->state->total_out, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     LAUNCH(K_EMIT, k_emit, ns, EMIT_THREADS, 0, st, d_in, (long long)n, (long long)s0, (long long)(nseg - 1),
            is_final, prm, ctx->tokens, ctx->A, d_out, (unsigned long long)out_cap, ctx->state);
     return DFL_OK;
@@ -1954,6 +2350,8 @@ extern "C" int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_
     if (chunk_segs > nseg) chunk_segs = nseg;
     if (chunk_segs < 1) chunk_segs = 1;
     int rc = ensure_ws(ctx, chunk_segs);
+    if (rc) return rc;
+    rc = ensure_index(ctx, nseg);
     if (rc) return rc;
     ctx->ev_n = 0;
     ctx->last_n = (long long)n;
@@ -2093,6 +2491,9 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
          * on three streams; output offsets stay on the device, each piece's end offset comes back with it */
         int rc = ensure_ws(ctx, piece_segs);
         if (rc) return rc;
+        rc = ensure_index(ctx, nseg);
+        if (rc) return rc;
+        ctx->last_n = (long long)n;
         rc = host_pipe_init(ctx, npieces);
         if (rc) return rc;
         ctx->ev_n = 0;
@@ -2188,4 +2589,103 @@ extern "C" int dfl_b200_synth_random(uint8_t *d_out, size_t n, uint64_t seed, vo
     k_synth_random<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_out, (unsigned long long)n, (unsigned long long)seed);
     CK(cudaGetLastError());
     return DFL_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* segment index + inflate                                                   */
+/* ------------------------------------------------------------------------- */
+
+extern "C" long dfl_b200_seg_index(dfl_ctx *ctx, uint64_t *offsets, long cap)
+{
+    if (!ctx) return DFL_E_INVAL;
+    const long cnt = (long)ctx->seg_index_n + 1;
+    if (!ctx->seg_index) return DFL_E_INVAL;
+    if (offsets) {
+        if (cap < cnt) return DFL_E_SZ;
+        if (cudaSetDevice(ctx->device) != cudaSuccess ||
+            cudaMemcpy(offsets, ctx->seg_index, (size_t)cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return DFL_E_CUDA;
+        if (ctx->seg_index_n == 0) offsets[0] = 0;
+    }
+    return cnt;
+}
+
+extern "C" const uint64_t *dfl_b200_seg_index_device(dfl_ctx *ctx) { return ctx ? (const uint64_t *)ctx->seg_index : NULL; }
+
+extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size_t body_len, const uint64_t *d_seg_off,
+                                       size_t nseg, uint32_t seg_bytes, size_t hist_len, uint8_t *d_out, size_t n,
+                                       uint32_t *adler, void *stream)
+{
+    if (!ctx || (!d_body && body_len) || (!d_out && n) || (!d_seg_off && nseg)) return DFL_E_INVAL;
+    if (seg_bytes < 1 || seg_bytes > DFL_MAX_SEG) return DFL_E_RANGE;
+    if (nseg != (n ? (n + seg_bytes - 1) / seg_bytes : 0)) return DFL_E_INVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->inf_cap < nseg + 1) {
+        if (ctx->inf_progress) cudaFree(ctx->inf_progress);
+        ctx->inf_progress = NULL;
+        ctx->inf_cap = 0;
+        CK(cudaMalloc(&ctx->inf_progress, (nseg + 1) * sizeof(unsigned int)));
+        ctx->inf_cap = nseg + 1;
+    }
+    ctx->ev_n = 0;
+    CK(cudaMemsetAsync(ctx->state, 0, sizeof(DevState), st));
+    CK(cudaMemsetAsync(ctx->inf_progress, 0, (nseg + 1) * sizeof(unsigned int), st));
+    if (nseg) {
+        const unsigned int grid = (unsigned int)((nseg + INF_WARPS - 1) / INF_WARPS);
+        LAUNCH(K_INFLATE, k_inflate, grid, INF_WARPS * 32, 0, st, d_body, (unsigned long long)body_len,
+               (const unsigned long long *)d_seg_off, (long long)nseg, (int)seg_bytes, (long long)n, (long long)hist_len, d_out,
+               ctx->inf_progress, ctx->inf_progress + nseg, ctx->state);
+    }
+    LAUNCH(K_FINAL, k_final, 1, 32, 0, st, (long long)n, ctx->state);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_state, ctx->state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ctx->timing) {
+        for (int k = 0; k < K_NUM; k++) ctx->k_ms[k] = 0;
+        for (int i = 0; i + 1 < ctx->ev_n; i += 2) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+            ctx->k_ms[ctx->ev_class[i]] += ms;
+        }
+    }
+    if (ctx->h_state->error) return DFL_E_DATA;
+    if (adler) *adler = ctx->h_state->adler;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t in_len, const uint64_t *seg_off, size_t nseg,
+                                        uint32_t seg_bytes, uint8_t *out, size_t n)
+{
+    if (!ctx || !in || in_len < 6 || (!out && n) || (!seg_off && nseg)) return DFL_E_INVAL;
+    /* zlib wrapper: the checks of src/deflate_decompress.c:347-368 (CM = 8, window <= 32 KiB, FCHECK, no preset dictionary) */
+    if ((in[0] & 0x0F) != 8 || (in[0] >> 4) > 7 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return DFL_E_DATA;
+    CK(cudaSetDevice(ctx->device));
+    const size_t body_len = in_len - 6;
+    if (ctx->d_in_cap < in_len + 16) {
+        if (ctx->d_in) cudaFree(ctx->d_in);
+        ctx->d_in = NULL; ctx->d_in_cap = 0;
+        CK(cudaMalloc(&ctx->d_in, in_len + 16));
+        ctx->d_in_cap = in_len + 16;
+    }
+    if (ctx->d_out_cap < n + 16) {
+        if (ctx->d_out) cudaFree(ctx->d_out);
+        ctx->d_out = NULL; ctx->d_out_cap = 0;
+        CK(cudaMalloc(&ctx->d_out, n + 16));
+        ctx->d_out_cap = n + 16;
+    }
+    uint64_t *d_off = NULL;
+    CK(cudaMalloc(&d_off, (nseg + 1) * sizeof(uint64_t)));
+    cudaStream_t st = 0;
+    uint32_t adler = 1;
+    int rc = DFL_OK;
+    if (cudaMemcpyAsync(ctx->d_in, in, in_len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d_off, seg_off, (nseg + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = DFL_E_CUDA;
+    if (!rc) rc = dfl_b200_inflate_device(ctx, ctx->d_in + 2, body_len, d_off, nseg, seg_bytes, 0, ctx->d_out, n, &adler, st);
+    if (!rc && n && cudaMemcpy(out, ctx->d_out, n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = DFL_E_CUDA;
+    cudaFree(d_off);
+    if (rc) return rc;
+    const uint32_t want = ((uint32_t)in[in_len - 4] << 24) | ((uint32_t)in[in_len - 3] << 16) | ((uint32_t)in[in_len - 2] << 8) | in[in_len - 1];
+    return want == adler ? DFL_OK : DFL_E_DATA; /* RFC 1950: Adler-32 of the uncompressed data, MSB first */
 }

@@ -58,6 +58,7 @@ extern "C" {
 #define DFL_E_RANGE (-10)   /* E_RANGE */
 #define DFL_E_INVAL (-11)   /* E_INVAL */
 #define DFL_E_CUDA (-100)   /* CUDA runtime / driver / device failure */
+#define DFL_E_DATA (-((1 << 24) + 13)) /* -E_ZINV (src/include/deflate_errors.h:21): corrupt stream / wrong index / Adler-32 mismatch */
 
 typedef struct dfl_ctx dfl_ctx;
 
@@ -120,6 +121,26 @@ int dfl_b200_keep_tokens(dfl_ctx *ctx, int enable);
 long dfl_b200_num_segments(dfl_ctx *ctx);
 int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info);
 long dfl_b200_tokens(dfl_ctx *ctx, long seg, uint32_t *tokens, long cap);
+
+/*
+ * Segment index + segment-parallel inflate (the GPU half of the reference's
+ * deflate_decompress, src/deflate_decompress.c:371-409, for streams this library wrote).
+ * Every segment of the body starts byte aligned; the index is the byte offset of each segment in the
+ * DEFLATE body plus, as its last entry, the body length (nseg + 1 entries).  It belongs to the last
+ * compress call of the context.  With it the body inflates one warp per segment.
+ */
+long dfl_b200_seg_index(dfl_ctx *ctx, uint64_t *offsets, long cap); /* -> entries (nseg + 1); offsets may be NULL */
+const uint64_t *dfl_b200_seg_index_device(dfl_ctx *ctx);            /* the same array in device memory */
+/* d_body/d_out/d_seg_off are device pointers; d_out[-hist_len, 0) must hold the shard's history when the
+ * shard was compressed with one.  n = uncompressed length (nseg = ceil(n / seg_bytes)).  Returns the
+ * Adler-32 of the n bytes (of this shard alone, as dfl_b200_deflate_device does). */
+int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size_t body_len, const uint64_t *d_seg_off,
+                            size_t nseg, uint32_t seg_bytes, size_t hist_len, uint8_t *d_out, size_t n,
+                            uint32_t *adler, void *stream);
+/* Host buffers: a complete zlib stream (header + body + Adler-32) and its index -> n bytes; checks the
+ * header fields src/deflate_decompress.c:347-368 checks and the Adler-32 (:402-404). */
+int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t in_len, const uint64_t *seg_off, size_t nseg,
+                             uint32_t seg_bytes, uint8_t *out, size_t n);
 
 /* Which kernel resolves the greedy parse of a chunk: 0 = chosen by the chunk's segment count (default),
  * 1 = one warp per segment (k_parse_warp), 2 = one CTA per segment (k_parse).  Same tokens either way. */

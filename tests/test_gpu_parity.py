@@ -425,3 +425,93 @@ def test_parse_kernels_agree(D, O, mode, kind, seed, n):
         assert np.array_equal(comp.tokens(s), O.lz77_segment(data, 0, lo, hi, op)), f"mode {mode} segment {s}"
     assert z == O.zlib_compress(data, op)
     comp.close()
+
+
+# ---- segment index + GPU inflate ----
+
+def _gpu_roundtrip(D, data, **prm):
+    comp = D.Compressor(**prm)
+    z = comp.compress(data)
+    off = comp.seg_index()
+    seg = prm.get("seg_bytes", 32768)
+    nseg = (data.size + seg - 1) // seg
+    assert off.size == nseg + 1 and int(off[-1]) == len(z) - 6
+    assert all(int(off[i]) < int(off[i + 1]) for i in range(nseg)), "segments are non-empty and in order"
+    back = comp.decompress(z, off, data.size)
+    comp.close()
+    return z, off, back
+
+
+@pytest.mark.parametrize("kind,seed,n", [("markov", 21, 1), ("markov", 21, 2), ("markov", 21, 700), ("markov", 22, 32768),
+                                         ("markov", 23, 32769), ("markov", 24, 1000003), ("random", 25, 200001),
+                                         ("log", 26, 500000), ("png", 27, 400000), ("zeros", 0, 300000),
+                                         ("period7", 0, 100000), ("const_a", 0, 65536)])
+def test_gpu_inflate_roundtrip(D, kind, seed, n):
+    """compress -> (stream, segment index) -> k_inflate gives the input back, bit for bit, and the
+    stream is what zlib inflates too (so the GPU decoder reads standard DEFLATE)."""
+    data = make_input(kind, seed, 0, n)
+    z, off, back = _gpu_roundtrip(D, data)
+    assert back == data.tobytes()
+    assert zlib.decompress(z) == data.tobytes()
+
+
+@pytest.mark.parametrize("prm", [dict(seg_bytes=2048), dict(seg_bytes=16384, window=4096), dict(use_dict=0),
+                                 dict(block_mode=1), dict(block_mode=2), dict(block_mode=3), dict(chain_limit=4),
+                                 dict(seg_bytes=1000, window=32768)])
+def test_gpu_inflate_params(D, prm):
+    """Small segments (matches reaching many segments back), no dictionary, forced stored / fixed /
+    dynamic blocks."""
+    data = np.concatenate([make_input("markov", 31, 0, 150000), make_input("random", 32, 0, 30000),
+                           make_input("log", 33, 0, 120000)])
+    z, off, back = _gpu_roundtrip(D, data, **prm)
+    assert back == data.tobytes()
+
+
+def test_gpu_inflate_empty_and_errors(D):
+    comp = D.Compressor()
+    z = comp.compress(np.zeros(0, dtype=np.uint8))
+    off = comp.seg_index()
+    assert off.size == 1
+    assert comp.decompress(z, off, 0) == b""
+    data = make_input("markov", 41, 0, 200000)
+    z = comp.compress(data)
+    off = comp.seg_index()
+    assert comp.decompress(z, off, data.size) == data.tobytes()
+    bad = bytearray(z)
+    bad[len(bad) // 2] ^= 0x55  # corrupt the body: the decoder must fail (or the Adler-32 must), never hang
+    with pytest.raises(D.DflError):
+        comp.decompress(bytes(bad), off, data.size)
+    bad = bytearray(z)
+    bad[-1] ^= 1  # wrong Adler-32
+    with pytest.raises(D.DflError):
+        comp.decompress(bytes(bad), off, data.size)
+    bad_off = off.copy()
+    bad_off[2] += 3  # wrong index
+    with pytest.raises(D.DflError):
+        comp.decompress(z, bad_off, data.size)
+    assert comp.decompress(z, off, data.size) == data.tobytes()  # the context survives
+    comp.close()
+
+
+def test_gpu_inflate_device_large(D):
+    """64 MiB, device to device: inflate(compress(x)) == x and the Adler-32 values agree."""
+    import torch
+
+    n = 64 << 20
+    data = np.concatenate([make_input("markov", 51, 0, n // 2), make_input("png", 52, 0, n // 4),
+                           make_input("random", 53, 0, n // 8), make_input("log", 54, 0, n // 8)])
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(data).to(dev)
+    comp = D.Compressor()
+    cap = comp.bound(n)
+    d_z = torch.empty(cap, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    out_len, adler = comp.deflate_device(d_in.data_ptr(), n, 0, True, d_z.data_ptr(), cap, st)
+    nseg = n // 32768
+    d_off = torch.from_numpy(comp.seg_index().astype(np.int64)).to(dev)
+    d_back = torch.zeros(n, dtype=torch.uint8, device=dev)
+    adler2 = comp.inflate_device(d_z.data_ptr(), out_len, d_off.data_ptr(), nseg, d_back.data_ptr(), n, 0, st)
+    torch.cuda.synchronize()
+    assert adler2 == adler == (zlib.adler32(data.tobytes()) & 0xFFFFFFFF)
+    assert torch.equal(d_back, d_in)
+    comp.close()
