@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         L.dfl_b200_seg_index_device.argtypes = [vp]
         L.dfl_b200_inflate_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, C.c_size_t, vp, C.c_size_t,
                                               C.POINTER(C.c_uint32), vp]
+        L.dfl_b200_inflate_rounds.argtypes = [vp]
         L.dfl_b200_decompress_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp, C.c_size_t]
         L.dfl_b200_num_segments.restype = C.c_long
         L.dfl_b200_num_segments.argtypes = [vp]
@@ -225,6 +226,9 @@ class Compressor:
         if rc:
             raise DflError(rc, "dfl_b200_inflate_device")
         return int(adler.value)
+
+    def inflate_rounds(self) -> int:
+        return int(lib().dfl_b200_inflate_rounds(self._ctx))
 
     def decompress(self, z: bytes, seg_off: np.ndarray, n: int) -> bytes:
         """zlib stream + its segment index -> the n original bytes, inflated on the GPU (host buffers)."""

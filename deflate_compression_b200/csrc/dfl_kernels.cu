@@ -47,8 +47,8 @@
 #define DFL_CHUNK_BYTES (256u << 20)
 #define ADLER_MOD 65521u
 
-enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_INFLATE, K_NUM };
-static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final", "k_inflate"};
+enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_INFLATE, K_INF_RESOLVE, K_INF_FINISH, K_NUM };
+static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final", "k_inflate", "k_inf_resolve", "k_inf_finish"};
 
 struct DevState {
     unsigned long long total_out;  /* bytes of deflate body written so far */
@@ -58,6 +58,7 @@ struct DevState {
     unsigned int adler;            /* final Adler-32 */
     unsigned long long t_phase[24]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
     unsigned int sort_fallbacks;   /* segments whose index had to be rebuilt with the ballot-ranked scatter */
+    unsigned int inf_pending;      /* k_inf_resolve: some word is still a pointer */
 };
 
 struct SegArrays {
@@ -1648,18 +1649,22 @@ __global__ void k_synth_random(uint8_t *out, unsigned long long n, unsigned long
 /*
  * Segment-parallel inflate of a stream this library produced (the CPU
  * twin is host/deflate_decompress.c, the reference's is src/deflate_decompress.c:146-409).  Every
- * segment starts byte aligned at a known offset (the segment index k_scan computed), so one warp
- * decodes one segment: lane 0 runs the Huffman decoder (RFC 1951 3.2.3-3.2.7: stored, fixed and
- * dynamic blocks), literals are stored as they come, a match is copied by the whole warp.  A match
- * may reach into the output of earlier segments (dictionary priming on the compress side); those
- * bytes are written by other warps, so every warp publishes how much of its segment is complete
- * (release) and a reader waits for the bytes it needs (acquire).  Segments are handed out in the
- * order warps start (a ticket), so a warp only ever waits for warps that are already running.
+ * segment starts byte aligned at a known offset (the segment index k_scan computed), so the Huffman
+ * decoding of all segments runs in parallel, one warp per segment.  The LZ77 copies do not: with
+ * dictionary priming the head of every segment copies from the tail of the one before, a dependency
+ * chain through the whole stream.  So decoding and copying are separated (the multi-round resolution
+ * of Sitaridi et al., "Massively-parallel lossless data decompression"):
+ *   k_inflate     : per segment, lane 0 decodes (RFC 1951 3.2.3-3.2.7: stored, fixed, dynamic
+ *                   blocks); every output byte gets a 32-bit word -- 0x80000000 | value when it is
+ *                   known, else the distance back to the byte it copies.  Copies inside the segment
+ *                   are followed on the spot, so an unknown byte always points BEFORE its segment.
+ *   k_inf_resolve : pointer jumping, w[p] <- w[p - w[p]] (value, or the sum of the two distances);
+ *                   every round at least doubles the number of segments a pointer spans.
+ *   k_inf_finish  : words -> bytes, Adler-32 partial sums per segment.
  */
 #define INF_WARPS 4
 #define INF_LL_BITS 10
 #define INF_D_BITS 8
-#define INF_PUBLISH 1024 /* bytes between progress updates */
 
 struct InfTables {
     uint16_t ll[1 << INF_LL_BITS]; /* (symbol << 4) | length, 0 = longer than INF_LL_BITS */
@@ -1774,28 +1779,28 @@ __device__ bool inf_build(InfTables &T, int which, int base, int n, int lane)
     return ok;
 }
 
+#define INF_KNOWN 0x80000000u
+
 __global__ void __launch_bounds__(INF_WARPS * 32)
 k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const unsigned long long *__restrict__ seg_off,
-          long long nseg, int seg_bytes, long long n, long long hist_len, uint8_t *d_out, unsigned int *progress,
-          unsigned int *ticket, DevState *state)
+          long long seg0, int ns, int seg_bytes, long long n, long long hist_len, uint32_t *w, DevState *state)
 {
     __shared__ InfTables s_tab[INF_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     InfTables &T = s_tab[warp];
-    long long s = 0;
-    if (lane == 0) s = (long long)atomicAdd(ticket, 1u);
-    s = __shfl_sync(FULL, s, 0);
-    if (s >= nseg) return;
+    const int sl = blockIdx.x * INF_WARPS + warp;
+    if (sl >= ns) return;
+    const long long s = seg0 + sl;
     const long long seg_lo = s * seg_bytes;
     const int seglen = (int)(((seg_lo + seg_bytes < n) ? seg_lo + seg_bytes : n) - seg_lo);
-    uint8_t *out = d_out + seg_lo;
+    uint32_t *out = w + (size_t)sl * seg_bytes;
     const unsigned long long a0 = (unsigned long long)((uintptr_t)body & 3);
     BitReader br;
     br.words = reinterpret_cast<const uint32_t *>(body - a0);
     br.nwords = (body_len + a0 + 3) >> 2;
     const unsigned long long seg_end = seg_off[s + 1] + a0;
     if (lane == 0) br.init(seg_off[s] + a0);
-    int pos = 0, pub = 0;
+    int pos = 0;
     int err = 0;
 
     for (;;) {
@@ -1824,9 +1829,9 @@ k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const u
             len = __shfl_sync(FULL, len, 0);
             src = __shfl_sync(FULL, src, 0);
             err = __shfl_sync(FULL, err, 0);
-            if (err || pos + len > seglen) { err = 1; break; }
+            if (err || pos + len > seglen || src + (unsigned long long)len > body_len + a0) { err = 1; break; }
             const uint8_t *sb = reinterpret_cast<const uint8_t *>(br.words) + src;
-            for (int t = lane; t < len; t += 32) out[pos + t] = __ldg(sb + t);
+            for (int t = lane; t < len; t += 32) out[pos + t] = INF_KNOWN | __ldg(sb + t);
             pos += len;
             __syncwarp();
             if (lane == 0) br.init(src + (unsigned long long)len);
@@ -1918,8 +1923,7 @@ k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const u
                         if (sym < 0) { mlen = -2; break; }
                         if (sym < 256) {
                             if (npos >= seglen) { mlen = -2; break; }
-                            out[npos++] = (uint8_t)sym;
-                            if (npos - pos >= INF_PUBLISH) break; /* mlen = 0: literals only, lets the warp publish progress */
+                            out[npos++] = INF_KNOWN | (uint32_t)sym;
                             continue;
                         }
                         if (sym == 256) { mlen = -1; break; }
@@ -1932,24 +1936,8 @@ k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const u
                         else ds = inf_slow(br, T, 1);
                         if (ds < 0 || ds > 29) { mlen = -2; break; }
                         mdist = c_dist_base[ds] + (int)br.get(c_dist_extra[ds]);
+                        if (seg_lo + npos - mdist < -hist_len) mlen = -2; /* reaches before the history the caller supplied */
                         break;
-                    }
-                    /* bytes of earlier segments this match reads must be complete */
-                    if (mlen > 0) {
-                        const long long g_src = seg_lo + npos - mdist;
-                        if (g_src < -hist_len) mlen = -2; /* reaches before the history the caller supplied */
-                        if (mlen > 0 && g_src < seg_lo) {
-                            long long need_hi = g_src + mlen < seg_lo ? g_src + mlen : seg_lo; /* exclusive */
-                            for (long long k = (g_src < 0 ? 0 : g_src / seg_bytes); k < s && k * seg_bytes < need_hi; k++) {
-                                const long long klo = k * seg_bytes;
-                                const unsigned int want = (unsigned int)((need_hi - klo < seg_bytes) ? need_hi - klo : seg_bytes);
-                                unsigned int got;
-                                do {
-                                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(progress + k) : "memory");
-                                    if (got < want && *(volatile unsigned int *)&state->error) { got = 0xFFFFFFFFu; mlen = -2; }
-                                } while (got < want);
-                            }
-                        }
                     }
                 }
                 mlen = __shfl_sync(FULL, mlen, 0);
@@ -1958,21 +1946,20 @@ k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const u
                 if (mlen == -1) break;                 /* end of block */
                 if (mlen < 0 || pos + mlen > seglen) { err = 1; break; }
                 __syncwarp(); /* lane 0's literals are ordered before the copy's reads */
-                /* copy: source bytes repeat with period mdist when the match overlaps itself */
-                if (mlen > 0) {
-                    const uint8_t *srcp = out + pos - mdist;
-                    for (int t = lane; t < mlen; t += 32) {
-                        const int so = mdist >= mlen ? t : t % mdist;
-                        out[pos + t] = __ldcg(srcp + so);
+                /* copy: the source repeats with period mdist when the match overlaps itself.  A source inside
+                 * the segment is already final-or-pointing-before-the-segment: follow it now. */
+                for (int t = lane; t < mlen; t += 32) {
+                    const int so = mdist >= mlen ? t : t % mdist;
+                    const int sp = pos - mdist + so;
+                    uint32_t v = (uint32_t)(pos + t - sp);
+                    if (sp >= 0) {
+                        const uint32_t a = __ldcg(out + sp);
+                        v = (a & INF_KNOWN) ? a : v + a;
                     }
+                    out[pos + t] = v;
                 }
                 pos += mlen;
                 __syncwarp();
-                if (lane == 0 && pos - pub >= INF_PUBLISH) {
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + s), "r"((unsigned int)pos) : "memory");
-                    pub = pos;
-                }
             }
             if (err) break;
         } else {
@@ -1986,30 +1973,79 @@ k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const u
     }
     if (!err && pos != seglen) err = 1;
     if (err && lane == 0) atomicExch(&state->error, 2u);
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(progress + s), "r"(err ? 0xFFFFFFFFu : (unsigned int)seglen) : "memory");
+}
+
+/* One round of pointer jumping over the cnt words of a chunk (chunk position 0 = output byte chunk_lo).
+ * Four words per thread and step; groups that are already all values cost one 16-byte read. */
+__device__ __forceinline__ uint32_t inf_jump(const uint32_t *w, long long p, uint32_t v, long long chunk_lo, const uint8_t *d_out)
+{
+    const long long q = p - (long long)v;
+    if (q < 0) return INF_KNOWN | d_out[chunk_lo + q]; /* an earlier chunk (or the caller's history): final bytes */
+    const uint32_t a = __ldcg(w + q);
+    return (a & INF_KNOWN) ? a : v + a;
+}
+
+__global__ void __launch_bounds__(256)
+k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, const uint8_t *__restrict__ d_out, unsigned int *pending)
+{
+    unsigned int left = 0;
+    const long long quads = cnt >> 2;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < quads; g += (long long)gridDim.x * blockDim.x) {
+        uint4 v = __ldcg(reinterpret_cast<const uint4 *>(w) + g);
+        if (v.x & v.y & v.z & v.w & INF_KNOWN) continue;
+        const long long p = g << 2;
+        if (!(v.x & INF_KNOWN)) v.x = inf_jump(w, p, v.x, chunk_lo, d_out);
+        if (!(v.y & INF_KNOWN)) v.y = inf_jump(w, p + 1, v.y, chunk_lo, d_out);
+        if (!(v.z & INF_KNOWN)) v.z = inf_jump(w, p + 2, v.z, chunk_lo, d_out);
+        if (!(v.w & INF_KNOWN)) v.w = inf_jump(w, p + 3, v.w, chunk_lo, d_out);
+        reinterpret_cast<uint4 *>(w)[g] = v;
+        left |= ~(v.x & v.y & v.z & v.w) & INF_KNOWN;
     }
-    /* Adler-32 partial sums of the segment (same bookkeeping as k_match) */
-    if (!err) {
-        uint32_t a = 0;
-        unsigned long long b = 0;
-        for (int i = lane; i < seglen; i += 32) {
-            const uint32_t v = __ldcg(out + i);
-            a += v;
-            b += (unsigned long long)v * (uint32_t)(seglen - i);
+    if (blockIdx.x == 0 && threadIdx.x < (cnt & 3)) {
+        const long long p = (quads << 2) + threadIdx.x;
+        const uint32_t v = __ldcg(w + p);
+        if (!(v & INF_KNOWN)) {
+            const uint32_t nv = inf_jump(w, p, v, chunk_lo, d_out);
+            w[p] = nv;
+            left |= ~nv & INF_KNOWN;
         }
-        for (int o = 16; o; o >>= 1) {
-            a += __shfl_xor_sync(FULL, a, o);
-            b += __shfl_xor_sync(FULL, b, o);
-        }
-        if (lane == 0) {
-            const unsigned long long am = a % ADLER_MOD;
-            const unsigned long long rest = (unsigned long long)(n - (seg_lo + seglen)) % ADLER_MOD;
-            atomicAdd(&state->adl_a, am);
-            atomicAdd(&state->adl_b, (b % ADLER_MOD + am * rest) % ADLER_MOD);
-        }
+    }
+    if (__any_sync(__activemask(), left != 0) && (threadIdx.x & 31) == 0) atomicOr(pending, 1u);
+}
+
+/* words -> bytes; Adler-32 partial sums of the segment (same bookkeeping as k_match) */
+__global__ void __launch_bounds__(256)
+k_inf_finish(const uint32_t *__restrict__ w, long long seg0, int seg_bytes, long long n, uint8_t *d_out, DevState *state)
+{
+    __shared__ uint32_t s_a[8];
+    __shared__ unsigned long long s_b[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long s = seg0 + blockIdx.x;
+    const long long seg_lo = s * seg_bytes;
+    const int seglen = (int)(((seg_lo + seg_bytes < n) ? seg_lo + seg_bytes : n) - seg_lo);
+    const uint32_t *ws = w + (size_t)blockIdx.x * seg_bytes;
+    uint32_t a = 0, bad = 0;
+    unsigned long long b = 0;
+    for (int i = tid; i < seglen; i += 256) {
+        const uint32_t v = ws[i];
+        bad |= !(v & INF_KNOWN);
+        const uint32_t byte = v & 0xFF;
+        d_out[seg_lo + i] = (uint8_t)byte;
+        a += byte;
+        b += (unsigned long long)byte * (uint32_t)(seglen - i);
+    }
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o);
+        b += __shfl_xor_sync(FULL, b, o);
+    }
+    if (lane == 0) { s_a[warp] = a; s_b[warp] = b; }
+    if (__syncthreads_or((int)bad) && tid == 0) atomicExch(&state->error, 3u);
+    if (tid == 0) {
+        for (int k = 1; k < 8; k++) { a += s_a[k]; b += s_b[k]; }
+        const unsigned long long am = a % ADLER_MOD;
+        const unsigned long long rest = (unsigned long long)(n - (seg_lo + seglen)) % ADLER_MOD;
+        atomicAdd(&state->adl_a, am);
+        atomicAdd(&state->adl_b, (b % ADLER_MOD + am * rest) % ADLER_MOD);
     }
 }
 
@@ -2040,8 +2076,9 @@ struct dfl_ctx {
     /* segment index of the last compress call (byte offset of every segment in the body, + the end) and inflate state */
     unsigned long long *seg_index;
     size_t seg_index_cap, seg_index_n;
-    unsigned int *inf_progress;
+    uint32_t *inf_w; /* inflate: one word per output byte of a chunk */
     size_t inf_cap;
+    int inf_rounds;
     /* bookkeeping */
     long launches;
     long long last_n;
@@ -2210,7 +2247,7 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
     if (ctx->seg_index) cudaFree(ctx->seg_index);
-    if (ctx->inf_progress) cudaFree(ctx->inf_progress);
+    if (ctx->inf_w) cudaFree(ctx->inf_w);
     for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
     free(ctx->e_in); free(ctx->e_done);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -2621,26 +2658,51 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
     if (nseg != (n ? (n + seg_bytes - 1) / seg_bytes : 0)) return DFL_E_INVAL;
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->inf_cap < nseg + 1) {
-        if (ctx->inf_progress) cudaFree(ctx->inf_progress);
-        ctx->inf_progress = NULL;
+    size_t chunk_segs = DFL_CHUNK_BYTES / (size_t)seg_bytes;
+    if (chunk_segs > nseg) chunk_segs = nseg;
+    if (chunk_segs < 1) chunk_segs = 1;
+    const size_t words = chunk_segs * seg_bytes;
+    if (ctx->inf_cap < words) {
+        if (ctx->inf_w) cudaFree(ctx->inf_w);
+        ctx->inf_w = NULL;
         ctx->inf_cap = 0;
-        CK(cudaMalloc(&ctx->inf_progress, (nseg + 1) * sizeof(unsigned int)));
-        ctx->inf_cap = nseg + 1;
+        CK(cudaMalloc(&ctx->inf_w, words * sizeof(uint32_t) + 16));
+        ctx->inf_cap = words;
     }
     ctx->ev_n = 0;
     CK(cudaMemsetAsync(ctx->state, 0, sizeof(DevState), st));
-    CK(cudaMemsetAsync(ctx->inf_progress, 0, (nseg + 1) * sizeof(unsigned int), st));
-    if (nseg) {
-        const unsigned int grid = (unsigned int)((nseg + INF_WARPS - 1) / INF_WARPS);
-        LAUNCH(K_INFLATE, k_inflate, grid, INF_WARPS * 32, 0, st, d_body, (unsigned long long)body_len,
-               (const unsigned long long *)d_seg_off, (long long)nseg, (int)seg_bytes, (long long)n, (long long)hist_len, d_out,
-               ctx->inf_progress, ctx->inf_progress + nseg, ctx->state);
+    unsigned int *pending = &ctx->state->inf_pending;
+    int rounds_total = 0;
+    for (size_t s0 = 0; s0 < nseg; s0 += chunk_segs) {
+        const int ns = (int)(nseg - s0 < chunk_segs ? nseg - s0 : chunk_segs);
+        const long long chunk_lo = (long long)(s0 * seg_bytes);
+        const long long cnt = (long long)((s0 + ns) * (size_t)seg_bytes < n ? (size_t)ns * seg_bytes : n - s0 * seg_bytes);
+        LAUNCH(K_INFLATE, k_inflate, (ns + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st, d_body, (unsigned long long)body_len,
+               (const unsigned long long *)d_seg_off, (long long)s0, ns, (int)seg_bytes, (long long)n, (long long)hist_len,
+               ctx->inf_w, ctx->state);
+        /* pointer jumping until no word is a pointer any more: every round at least doubles the number of
+         * segments a pointer spans, so ceil(log2(ns)) + 2 rounds always suffice */
+        int max_rounds = 3;
+        for (int v = ns; v > 1; v >>= 1) max_rounds++;
+        for (int r = 0;; r++) {
+            CK(cudaMemsetAsync(pending, 0, sizeof(unsigned int), st));
+            LAUNCH(K_INF_RESOLVE, k_inf_resolve, 148 * 16, 256, 0, st, ctx->inf_w, cnt, chunk_lo, (const uint8_t *)d_out, pending);
+            unsigned int left = 0;
+            CK(cudaMemcpyAsync(&ctx->h_state->inf_pending, pending, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            left = ctx->h_state->inf_pending;
+            rounds_total++;
+            if (!left) break;
+            if (r >= max_rounds) return DFL_E_DATA; /* a pointer cycle: not a stream this library wrote */
+        }
+        LAUNCH(K_INF_FINISH, k_inf_finish, ns, 256, 0, st, (const uint32_t *)ctx->inf_w, (long long)s0, (int)seg_bytes, (long long)n,
+               d_out, ctx->state);
     }
     LAUNCH(K_FINAL, k_final, 1, 32, 0, st, (long long)n, ctx->state);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_state, ctx->state, sizeof(DevState), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    ctx->inf_rounds = rounds_total;
     if (ctx->timing) {
         for (int k = 0; k < K_NUM; k++) ctx->k_ms[k] = 0;
         for (int i = 0; i + 1 < ctx->ev_n; i += 2) {
@@ -2653,6 +2715,9 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
     if (adler) *adler = ctx->h_state->adler;
     return DFL_OK;
 }
+
+/* pointer-jumping rounds of the last inflate call (profiling aid) */
+extern "C" int dfl_b200_inflate_rounds(dfl_ctx *ctx) { return ctx ? ctx->inf_rounds : 0; }
 
 extern "C" int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t in_len, const uint64_t *seg_off, size_t nseg,
                                         uint32_t seg_bytes, uint8_t *out, size_t n)

@@ -127,7 +127,8 @@ long dfl_b200_tokens(dfl_ctx *ctx, long seg, uint32_t *tokens, long cap);
  * deflate_decompress, src/deflate_decompress.c:371-409, for streams this library wrote).
  * Every segment of the body starts byte aligned; the index is the byte offset of each segment in the
  * DEFLATE body plus, as its last entry, the body length (nseg + 1 entries).  It belongs to the last
- * compress call of the context.  With it the body inflates one warp per segment.
+ * compress call of the context.  With it the Huffman decoding runs one warp per segment; the LZ77 copies,
+ * which chain from segment to segment, are resolved by pointer jumping (see k_inflate).
  */
 long dfl_b200_seg_index(dfl_ctx *ctx, uint64_t *offsets, long cap); /* -> entries (nseg + 1); offsets may be NULL */
 const uint64_t *dfl_b200_seg_index_device(dfl_ctx *ctx);            /* the same array in device memory */
@@ -137,6 +138,7 @@ const uint64_t *dfl_b200_seg_index_device(dfl_ctx *ctx);            /* the same 
 int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size_t body_len, const uint64_t *d_seg_off,
                             size_t nseg, uint32_t seg_bytes, size_t hist_len, uint8_t *d_out, size_t n,
                             uint32_t *adler, void *stream);
+int dfl_b200_inflate_rounds(dfl_ctx *ctx); /* pointer-jumping rounds of the last inflate call */
 /* Host buffers: a complete zlib stream (header + body + Adler-32) and its index -> n bytes; checks the
  * header fields src/deflate_decompress.c:347-368 checks and the Adler-32 (:402-404). */
 int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t in_len, const uint64_t *seg_off, size_t nseg,
