@@ -302,13 +302,31 @@ def run_gpu(args) -> None:
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
 
+    # ---- the way back: segment-parallel inflate of what the timed step wrote, device to
+    # device, compared with the shard on the device.  Not part of `value`; reported beside it. ----
+    out_len, adler = step(with_gather=False)
+    d_off = torch.from_numpy(comp.seg_index().astype(np.int64)).to(dev)
+    d_back = torch.zeros(hist + n, dtype=torch.uint8, device=dev)
+    d_back[:hist].copy_(d_buf[:hist])
+    nseg = (n + 32767) // 32768
+    inf_ms = []
+    for _ in range(3):
+        adler_back = comp.inflate_device(d_out.data_ptr(), out_len, d_off.data_ptr(), nseg, d_back.data_ptr() + hist, n,
+                                         hist, stream)
+        k = comp.kernel_ms()
+        inf_ms.append(k["k_inflate"] + k["k_inf_resolve"] + k["k_inf_finish"])
+    inflate_ok = bool(adler_back == adler) and bool(torch.equal(d_back[hist:], d_buf[hist:]))
+    inflate_rounds = comp.inflate_rounds()
+    comp.enqueue(d_in, n, hist, is_final, d_out.data_ptr(), cap, stream)  # leave the per-kernel times of a compress step behind
+    comp.finish(stream)
+
     # ---- reduce over ranks: max time ----
-    t = torch.tensor([ms, ms_nogather, te * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_nogather, te * 1e3, min(inf_ms), 0.0 if inflate_ok else 1.0], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(n), float(out_len)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_nogather, te_ms = t.tolist()
+    ms, ms_nogather, te_ms, inf_best_ms, inf_bad = t.tolist()
     n_total, out_total = tot.tolist()
 
     if rank == 0:
@@ -341,6 +359,9 @@ def run_gpu(args) -> None:
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": km},
         }
+        line["inflate"] = {"value": n_total / (inf_best_ms * 1e-3) / 1e9, "unit": "GB/s of output (device-timed, k_inflate + "
+                           "k_inf_resolve + k_inf_finish, best of 3)", "ms": inf_best_ms, "pointer_jumping_rounds": inflate_rounds,
+                           "roundtrip_ok": inf_bad == 0.0}
         if world > 1:
             line["compress_only_value"] = n_total * args.steps / (ms_nogather * 1e-3) / 1e9
         # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's single-threaded compressor ----
