@@ -1146,18 +1146,26 @@ __device__ void huff_lengths_warp(const uint32_t *freq, int n, int limit, uint8_
         m = 2;
         __syncwarp();
     }
-    /* rank sort by key = weight << 9 | symbol (keys are distinct) */
-    for (int s = lane; s < n; s += 32) {
-        uint32_t ws = sc.w[s];
-        if (!ws) continue;
-        unsigned long long key = ((unsigned long long)ws << 9) | (uint32_t)s;
-        int r = 0;
-        for (int j = 0; j < n; j++) {
-            uint32_t wj = sc.w[j];
-            r += (wj != 0) && ((((unsigned long long)wj << 9) | (uint32_t)j) < key);
+    /* rank sort by key = weight << 9 | symbol (keys are distinct; weights are token counts < 2^16).
+     * The used symbols are compacted first (sc.iw is free until the merge): m, not n, keys to rank. */
+    {
+        const uint32_t lt = lanemask_lt();
+        int base = 0;
+        for (int s0 = 0; s0 < n; s0 += 32) {
+            const int s = s0 + lane;
+            const uint32_t ws = s < n ? sc.w[s] : 0u;
+            const uint32_t mask = __ballot_sync(FULL, ws != 0);
+            if (ws) sc.iw[base + __popc(mask & lt)] = (ws << 9) | (uint32_t)s;
+            base += __popc(mask);
         }
-        sc.sw[r] = ws;
-        sc.ssym[r] = (uint16_t)s;
+        __syncwarp();
+        for (int r0 = lane; r0 < m; r0 += 32) {
+            const uint32_t key = sc.iw[r0];
+            int r = 0;
+            for (int j = 0; j < m; j++) r += sc.iw[j] < key;
+            sc.sw[r] = key >> 9;
+            sc.ssym[r] = (uint16_t)(key & 511u);
+        }
     }
     __syncwarp();
     if (lane == 0) {
@@ -2513,7 +2521,11 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
     const size_t nseg = n ? (n + prm.seg_bytes - 1) / prm.seg_bytes : 0;
     size_t piece_segs = HOST_PIPE_BYTES / (size_t)prm.seg_bytes;
     if (piece_segs < 1) piece_segs = 1;
-    const int npieces = (int)((nseg + piece_segs - 1) / piece_segs);
+    /* the first piece is a quarter piece: the kernels start after 8 MiB have arrived instead of 32 */
+    const size_t first_segs = piece_segs / 4 ? piece_segs / 4 : 1;
+    const int npieces = nseg <= first_segs ? (nseg ? 1 : 0) : 1 + (int)((nseg - first_segs + piece_segs - 1) / piece_segs);
+#define PIECE_S0(i) ((i) == 0 ? (size_t)0 : first_segs + (size_t)((i) - 1) * piece_segs)
+#define PIECE_S1(i) (PIECE_S0((i) + 1) < nseg ? PIECE_S0((i) + 1) : nseg)
     if (ctx->keep || npieces < 2) {
         /* small input, or the token-keeping debug path: one copy in, one call, one copy out */
         cudaStream_t st = 0;
@@ -2537,16 +2549,16 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
         ctx->nseg_kept = 0;
         CK(cudaMemsetAsync(ctx->state, 0, sizeof(DevState), ctx->s_run));
         for (int i = 0; i < npieces; i++) {
-            const size_t lo = (size_t)i * piece_segs * prm.seg_bytes;
-            const size_t hi = (lo + piece_segs * prm.seg_bytes < n) ? lo + piece_segs * prm.seg_bytes : n;
+            const size_t lo = PIECE_S0(i) * prm.seg_bytes;
+            const size_t hi = (PIECE_S1(i) * prm.seg_bytes < n) ? PIECE_S1(i) * prm.seg_bytes : n;
             CK(cudaMemcpyAsync(ctx->d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_in));
             CK(cudaEventRecord(ctx->e_in[i], ctx->s_in));
         }
         size_t copied = 0;
         for (int i = 0; i <= npieces; i++) {
             if (i < npieces) {
-                const size_t s0 = (size_t)i * piece_segs;
-                const int ns = (int)(nseg - s0 < piece_segs ? nseg - s0 : piece_segs);
+                const size_t s0 = PIECE_S0(i);
+                const int ns = (int)(PIECE_S1(i) - s0);
                 CK(cudaStreamWaitEvent(ctx->s_run, ctx->e_in[i], 0));
                 rc = launch_chunk(ctx, ctx->d_in, n, 0, 1, s0, ns, nseg, d_body, bound, ctx->s_run);
                 if (rc) return rc;
@@ -2577,6 +2589,8 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
         body = (size_t)ctx->h_state->total_out;
         adler = ctx->h_state->adler;
     }
+#undef PIECE_S0
+#undef PIECE_S1
     out[0] = 0x78; /* CM = 8, CINFO = 7: header the decoder checks at src/deflate_decompress.c:352-360 */
     out[1] = 0x9C;
     out[2 + body + 0] = (uint8_t)(adler >> 24); /* RFC 1950: Adler-32 MSB first */
