@@ -515,3 +515,61 @@ def test_gpu_inflate_device_large(D):
     assert adler2 == adler == (zlib.adler32(data.tobytes()) & 0xFFFFFFFF)
     assert torch.equal(d_back, d_in)
     comp.close()
+
+
+def _structured(rng, n):
+    """Bytes with the structures an LZ77 search has to get right: runs, short periods, far repeats just
+    inside / outside the window, repeats across segment boundaries, text, noise."""
+    out = bytearray()
+    pool = [bytes(rng.integers(0, 256, rng.integers(3, 400), dtype=np.uint8)) for _ in range(6)]
+    while len(out) < n:
+        r = rng.integers(0, 8)
+        if r == 0:
+            out += bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 700))
+        elif r == 1:
+            p = bytes(rng.integers(97, 123, rng.integers(1, 9), dtype=np.uint8))
+            out += p * int(rng.integers(1, 200))
+        elif r == 2 and len(out) > 10:
+            d = int(rng.integers(1, min(len(out), 40000)))
+            ln = int(rng.integers(3, 600))
+            for _ in range(ln):  # overlapping copy, like an LZ77 match
+                out.append(out[-d])
+        elif r == 3:
+            out += pool[int(rng.integers(0, len(pool)))]
+        elif r == 4:
+            out += bytes(rng.integers(0, 256, rng.integers(1, 3000), dtype=np.uint8))
+        elif r == 5:
+            out += bytes(rng.integers(0, 4, rng.integers(1, 2000), dtype=np.uint8))
+        elif r == 6 and len(out) > 32768:
+            d = int(rng.integers(32760, 32776))  # around the window edge
+            if d <= len(out):
+                out += out[-d:len(out) - d + int(rng.integers(3, 300))]
+        else:
+            out += bytes(rng.integers(32, 127, rng.integers(1, 500), dtype=np.uint8))
+    return np.frombuffer(bytes(out[:n]), dtype=np.uint8).copy()
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_structured_inputs(D, O, seed):
+    """Seeded fuzz: structured inputs x random parameters; tokens, stream bytes and both inflaters
+    (CPU and GPU) must agree with the oracle / the input."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([1, 7, 300, 5000, 32768, 40000, 70001, 150000, 260000]))
+    data = _structured(rng, n)
+    prm = {}
+    if rng.integers(0, 3) == 0:
+        prm["seg_bytes"] = int(rng.choice([512, 4096, 20000, 32768]))
+    if rng.integers(0, 3) == 0:
+        prm["window"] = int(rng.choice([1, 300, 4096, 32768]))
+    if rng.integers(0, 4) == 0:
+        prm["use_dict"] = 0
+    if rng.integers(0, 4) == 0:
+        prm["chain_limit"] = int(rng.choice([1, 5, 64]))
+    if rng.integers(0, 4) == 0:
+        prm["block_mode"] = int(rng.integers(0, 4))
+    z = check_stream(D, O, data, **prm)
+    comp = D.Compressor(**prm)
+    z2 = comp.compress(data)
+    assert z2 == z
+    assert comp.decompress(z2, comp.seg_index(), data.size) == data.tobytes()
+    comp.close()
