@@ -276,7 +276,7 @@ class Compressor:
 
     def phase_cycles(self) -> dict:
         names = ("stage_in", "build", "search", "total", "sort1", "park", "sort2", "offsets", "s1_count", "s1_scan", "s1_scatter", "d11",
-                 "sx_iter", "sx_walk", "sx_fin", "sx_done", "sx_cand", "sx_heads", "sx_hops", "sx_seek", "plain_segments")
+                 "sx_iter", "sx_walk", "sx_fin", "sx_done", "sx_cand", "sx_heads", "sx_hops", "sx_seek", "plain_segments", "warp_end_avg", "warp_end_max")
         return {nm: int(lib().dfl_b200_phase_cycles(self._ctx, k)) for k, nm in enumerate(names)}
 
     def sort_fallbacks(self) -> int:

@@ -697,13 +697,25 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             }                                                                           \
         } while (0)
 
+#ifdef DFL_SEARCH_STATS
+        unsigned long long sx_iter = 0, sx_walk = 0, sx_fin = 0, sx_done = 0, sx_cand = 0, sx_heads = 0, sx_hops = 0, sx_seek = 0;
+#endif
         for (;;) {
+#ifdef DFL_SEARCH_STATS
+            {
+                const uint32_t c1 = __reduce_add_sync(FULL, (st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) | (st == ST_DONE ? 0x10000u : 0u));
+                sx_iter++; sx_walk += c1 & 0xFF; sx_fin += (c1 >> 8) & 0xFF; sx_done += c1 >> 16;
+            }
+#endif
             /* phase A: walk the bucket backwards until a candidate passes the 4-byte filter */
             if (st == ST_WALK) {
 #pragma unroll 1
                 for (int t = 0; t < HOP_BATCH; t++) {
                     if (k <= k_lo || (HAS_K && hops >= K)) { st = ST_DONE; break; }
                     q = (int)lds_u16(lbase + 2 * (--k));
+#ifdef DFL_SEARCH_STATS
+                    sx_hops++;
+#endif
                     if (p - q > W) { st = ST_DONE; break; }
                     if (HAS_K) hops++;
                     /* filter: the 4 bytes ending at offset best_len (fmask0 while nothing is found
@@ -711,6 +723,9 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
                 }
             }
+#ifdef DFL_SEARCH_STATS
+            sx_cand += __reduce_add_sync(FULL, st == ST_CAND ? 1u : 0u);
+#endif
             /* a long remainder of the bucket is walked by the whole warp together (phase C) */
             if (st == ST_WALK) {
                 int rem = k - k_lo;
@@ -842,6 +857,9 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                         adv = best_len;
                     }
                     out[i] = t;
+#ifdef DFL_SEARCH_STATS
+                    sx_heads++;
+#endif
                     st = ST_IDLE;
                     const int ni = i + adv;
                     if (ni < seglen) {
@@ -865,6 +883,9 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                 /* the new heads find their own slot in their bucket together: lower bound of p in
                  * list[k, k_hi); candidates are then k-1 ... k_lo */
                 if (st == ST_SEEK) {
+#ifdef DFL_SEARCH_STATS
+                    sx_seek++;
+#endif
                     while (k < k_hi) {
                         const int mid = (k + k_hi) >> 1;
                         if ((int)lds_u16(lbase + 2 * mid) < p) k = mid + 1; else k_hi = mid;
@@ -873,9 +894,28 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                 }
             }
         }
+#ifdef DFL_SEARCH_STATS
+        sx_heads = __reduce_add_sync(FULL, (uint32_t)sx_heads);
+        sx_hops = __reduce_add_sync(FULL, (uint32_t)sx_hops);
+        sx_seek = __reduce_add_sync(FULL, (uint32_t)sx_seek);
+        if (lane == 0) {
+            atomicAdd(&state->t_phase[12], sx_iter); atomicAdd(&state->t_phase[13], sx_walk);
+            atomicAdd(&state->t_phase[14], sx_fin); atomicAdd(&state->t_phase[15], sx_done);
+            atomicAdd(&state->t_phase[16], sx_cand); atomicAdd(&state->t_phase[17], sx_heads);
+            atomicAdd(&state->t_phase[18], sx_hops); atomicAdd(&state->t_phase[19], sx_seek);
+            S.scan_w[warp] = (uint32_t)(clock64() - t2); /* when this warp ran out of work */
+        }
+#endif
 #undef INIT_HEAD
     }
     __syncthreads();
+#ifdef DFL_SEARCH_STATS
+    if (warp == 0 && warp < SEARCH_WARPS) {
+        const uint32_t e = lane < SEARCH_WARPS ? S.scan_w[lane] : 0u;
+        const uint32_t mx = __reduce_max_sync(FULL, e), sm = __reduce_add_sync(FULL, e);
+        if (lane == 0) { atomicAdd(&state->t_phase[21], (unsigned long long)(sm / SEARCH_WARPS)); atomicAdd(&state->t_phase[22], (unsigned long long)mx); }
+    }
+#endif
     if (warp == 0) {
         uint32_t a = S.red_a[lane];
         unsigned long long b = S.red_b[lane];
