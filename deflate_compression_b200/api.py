@@ -91,6 +91,11 @@ def lib() -> C.CDLL:
         L.dfl_b200_inflate_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, C.c_size_t, vp, C.c_size_t,
                                               C.POINTER(C.c_uint32), vp]
         L.dfl_b200_inflate_rounds.argtypes = [vp]
+        L.dfl_b200_png_filter_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, vp, vp]
+        L.dfl_b200_png_bound.restype = C.c_size_t
+        L.dfl_b200_png_bound.argtypes = [C.POINTER(DflParams), C.c_uint32, C.c_uint32, C.c_uint32]
+        L.dfl_b200_png_encode_host.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, C.c_size_t,
+                                               C.POINTER(C.c_size_t)]
         L.dfl_b200_decompress_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp, C.c_size_t]
         L.dfl_b200_num_segments.restype = C.c_long
         L.dfl_b200_num_segments.argtypes = [vp]
@@ -240,6 +245,26 @@ class Compressor:
         if rc:
             raise DflError(rc, "dfl_b200_decompress_host")
         return out[:n].tobytes()
+
+    # ---- PNG scanline filter + container ----
+    def png_filter_device(self, d_pix: int, row_bytes: int, rows: int, bpp: int, d_out: int, mode: int = 0,
+                          stream: int = 0) -> None:
+        rc = lib().dfl_b200_png_filter_device(self._ctx, d_pix, row_bytes, rows, bpp, mode, d_out, stream)
+        if rc:
+            raise DflError(rc, "dfl_b200_png_filter_device")
+
+    def png_encode(self, img: np.ndarray, filter_mode: int = 0) -> bytes:
+        """(h, w) or (h, w, c) uint8 pixels, c in 1..4 -> PNG file bytes (filter + deflate on the GPU)."""
+        a = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = a.shape[0], a.shape[1]
+        c = a.shape[2] if a.ndim == 3 else 1
+        cap = int(lib().dfl_b200_png_bound(C.byref(self.params), w, h, c))
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = lib().dfl_b200_png_encode_host(self._ctx, a.ctypes.data, w, h, c, filter_mode, out.ctypes.data, cap, C.byref(n))
+        if rc:
+            raise DflError(rc, "dfl_b200_png_encode_host")
+        return out[:n.value].tobytes()
 
     def set_parse_mode(self, mode: int) -> None:
         """0 = by segment count, 1 = warp per segment, 2 = CTA per segment (same tokens)."""

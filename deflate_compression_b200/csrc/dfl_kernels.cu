@@ -47,8 +47,8 @@
 #define DFL_CHUNK_BYTES (256u << 20)
 #define ADLER_MOD 65521u
 
-enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_INFLATE, K_INF_RESOLVE, K_INF_FINISH, K_NUM };
-static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final", "k_inflate", "k_inf_resolve", "k_inf_finish"};
+enum { K_MATCH = 0, K_PARSE, K_HUFF, K_SCAN, K_EMIT, K_FINAL, K_INFLATE, K_INF_RESOLVE, K_INF_FINISH, K_PNG_FILTER, K_NUM };
+static const char *k_names[K_NUM] = {"k_match", "k_parse", "k_huff", "k_scan", "k_emit", "k_final", "k_inflate", "k_inf_resolve", "k_inf_finish", "k_png_filter"};
 
 struct DevState {
     unsigned long long total_out;  /* bytes of deflate body written so far */
@@ -2098,6 +2098,65 @@ k_inf_finish(const uint32_t *__restrict__ w, long long seg0, int seg_bytes, long
 }
 
 /* ------------------------------------------------------------------------- */
+/* k_png_filter                                                              */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * PNG scanline filtering ahead of the compressor: the forward direction of
+ * the reference's defilter() (src/png/png_decoder.c:819-857; filter ids src/png/include/png_decoder.h:57-61;
+ * the Paeth predictor is the PNG specification's -- the reference's, :803-817, never sets pb / pc).
+ * One warp per row, two sweeps: the sums of |residual as a signed byte| of the five filter types, then the
+ * row filtered with the first type of minimal sum (mode 0) or with type mode - 1.  Rows only read the
+ * unfiltered row above, so all rows run in parallel.  HBM: the row and the row above read (the second
+ * sweep and the neighbouring warp hit L1/L2), the row written: ~3 B per pixel byte.
+ */
+#define PNGF_WARPS 8
+
+__device__ __forceinline__ int png_paeth(int a, int b, int c)
+{
+    const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+__global__ void __launch_bounds__(PNGF_WARPS * 32)
+k_png_filter(const uint8_t *__restrict__ pix, long long row_bytes, long long rows, int bpp, int mode, uint8_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long y = (long long)blockIdx.x * PNGF_WARPS + warp;
+    if (y >= rows) return;
+    const uint8_t *cur = pix + y * row_bytes, *prev = cur - row_bytes;
+    const bool has_prev = y > 0;
+    uint8_t *o = out + y * (row_bytes + 1);
+    int type = mode ? mode - 1 : 0;
+    if (!mode) {
+        uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        for (long long x = lane; x < row_bytes; x += 32) {
+            const int v = cur[x], a = x >= bpp ? cur[x - bpp] : 0, b = has_prev ? prev[x] : 0, c = (has_prev && x >= bpp) ? prev[x - bpp] : 0;
+            const uint32_t r0 = (uint8_t)v, r1 = (uint8_t)(v - a), r2 = (uint8_t)(v - b), r3 = (uint8_t)(v - ((a + b) >> 1)),
+                           r4 = (uint8_t)(v - png_paeth(a, b, c));
+            s0 += r0 < 128 ? r0 : 256 - r0;
+            s1 += r1 < 128 ? r1 : 256 - r1;
+            s2 += r2 < 128 ? r2 : 256 - r2;
+            s3 += r3 < 128 ? r3 : 256 - r3;
+            s4 += r4 < 128 ? r4 : 256 - r4;
+        }
+        s0 = __reduce_add_sync(FULL, s0); s1 = __reduce_add_sync(FULL, s1); s2 = __reduce_add_sync(FULL, s2);
+        s3 = __reduce_add_sync(FULL, s3); s4 = __reduce_add_sync(FULL, s4);
+        uint32_t best = s0;
+        if (s1 < best) { best = s1; type = 1; }
+        if (s2 < best) { best = s2; type = 2; }
+        if (s3 < best) { best = s3; type = 3; }
+        if (s4 < best) { best = s4; type = 4; }
+    }
+    if (lane == 0) o[0] = (uint8_t)type;
+    for (long long x = lane; x < row_bytes; x += 32) {
+        const int v = cur[x], a = x >= bpp ? cur[x - bpp] : 0, b = has_prev ? prev[x] : 0, c = (has_prev && x >= bpp) ? prev[x - bpp] : 0;
+        const int pred = type == 0 ? 0 : type == 1 ? a : type == 2 ? b : type == 3 ? (a + b) >> 1 : png_paeth(a, b, c);
+        o[1 + x] = (uint8_t)(v - pred);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* host side: context + C-ABI                                                */
 /* ------------------------------------------------------------------------- */
 
@@ -2124,6 +2183,8 @@ struct dfl_ctx {
     /* segment index of the last compress call (byte offset of every segment in the body, + the end) and inflate state */
     unsigned long long *seg_index;
     size_t seg_index_cap, seg_index_n;
+    uint8_t *d_png; /* PNG encode: the filtered scanlines */
+    size_t d_png_cap;
     uint32_t *inf_w; /* inflate: one word per output byte of a chunk */
     size_t inf_cap;
     int inf_rounds;
@@ -2296,6 +2357,7 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
     if (ctx->seg_index) cudaFree(ctx->seg_index);
     if (ctx->inf_w) cudaFree(ctx->inf_w);
+    if (ctx->d_png) cudaFree(ctx->d_png);
     for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
     free(ctx->e_in); free(ctx->e_done);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -2718,6 +2780,7 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
     const size_t words = chunk_segs * seg_bytes;
     if (ctx->inf_cap < words) {
         if (ctx->inf_w) cudaFree(ctx->inf_w);
+    if (ctx->d_png) cudaFree(ctx->d_png);
         ctx->inf_w = NULL;
         ctx->inf_cap = 0;
         CK(cudaMalloc(&ctx->inf_w, words * sizeof(uint32_t) + 16));
@@ -2807,4 +2870,117 @@ extern "C" int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t 
     if (rc) return rc;
     const uint32_t want = ((uint32_t)in[in_len - 4] << 24) | ((uint32_t)in[in_len - 3] << 16) | ((uint32_t)in[in_len - 2] << 8) | in[in_len - 1];
     return want == adler ? DFL_OK : DFL_E_DATA; /* RFC 1950: Adler-32 of the uncompressed data, MSB first */
+}
+
+/* ------------------------------------------------------------------------- */
+/* PNG: scanline filter + container                                          */
+/* ------------------------------------------------------------------------- */
+
+extern "C" int dfl_b200_png_filter_device(dfl_ctx *ctx, const uint8_t *d_pix, size_t row_bytes, size_t rows, int bpp, int mode,
+                                          uint8_t *d_out, void *stream)
+{
+    if (!ctx || ((!d_pix || !d_out) && rows && row_bytes)) return DFL_E_INVAL;
+    if (bpp < 1 || bpp > 8 || mode < 0 || mode > 5) return DFL_E_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(ctx->device));
+    ctx->ev_n = 0;
+    if (rows && row_bytes)
+        LAUNCH(K_PNG_FILTER, k_png_filter, (unsigned int)((rows + PNGF_WARPS - 1) / PNGF_WARPS), PNGF_WARPS * 32, 0, st, d_pix,
+               (long long)row_bytes, (long long)rows, bpp, mode, d_out);
+    CK(cudaGetLastError());
+    if (ctx->timing) {
+        CK(cudaStreamSynchronize(st));
+        for (int k = 0; k < K_NUM; k++) ctx->k_ms[k] = 0;
+        for (int i = 0; i + 1 < ctx->ev_n; i += 2) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+            ctx->k_ms[ctx->ev_class[i]] += ms;
+        }
+    }
+    return DFL_OK;
+}
+
+/* CRC-32 of a PNG chunk (calc_crc, src/include/crc.h:22-30) */
+static uint32_t png_crc(const uint8_t *p, size_t n)
+{
+    static uint32_t table[256];
+    static int ready = 0;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+            table[i] = c;
+        }
+        ready = 1;
+    }
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return ~c;
+}
+
+static void put_be32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+
+extern "C" size_t dfl_b200_png_bound(const dfl_params *prm, uint32_t width, uint32_t height, uint32_t channels)
+{
+    const size_t filtered = (size_t)height * ((size_t)width * channels + 1);
+    return dfl_b200_bound(prm, filtered) + 6 + 8 + 25 + 12 + 12;
+}
+
+/* 8-bit grey (1), grey + alpha (2), RGB (3) or RGBA (4) pixels -> a PNG file: signature, IHDR, one IDAT
+ * (filter on the GPU, compress on the GPU, zlib wrapper), IEND -- what src/png/png_decoder.c reads. */
+extern "C" int dfl_b200_png_encode_host(dfl_ctx *ctx, const uint8_t *pix, uint32_t width, uint32_t height, uint32_t channels,
+                                        int filter_mode, uint8_t *out, size_t cap, size_t *out_len)
+{
+    static const uint8_t sig[8] = {0x89, 0x50, 0x4E, 0x47, 0x0D, 0x0A, 0x1A, 0x0A}; /* PNG_HEAD, src/png/include/png_decoder.h:63 */
+    static const uint8_t ctype[5] = {0, 0, 4, 2, 6};
+    if (!ctx || !pix || !out || !out_len) return DFL_E_INVAL;
+    if (!width || !height || channels < 1 || channels > 4) return DFL_E_RANGE;
+    const size_t row_bytes = (size_t)width * channels, npix = row_bytes * height, nf = (size_t)height * (row_bytes + 1);
+    if (nf + 64 > 0x7FFFFFFFull) return DFL_E_RANGE; /* one IDAT chunk */
+    CK(cudaSetDevice(ctx->device));
+    const dfl_params prm = ctx->prm;
+    const size_t bound = dfl_b200_bound(&prm, nf);
+    if (cap < 8 + 25 + 12 + 12) return DFL_E_SZ;
+    if (ctx->d_in_cap < npix + 16) {
+        if (ctx->d_in) cudaFree(ctx->d_in);
+        ctx->d_in = NULL; ctx->d_in_cap = 0;
+        CK(cudaMalloc(&ctx->d_in, npix + 16));
+        ctx->d_in_cap = npix + 16;
+    }
+    if (ctx->d_png_cap < nf + 16) {
+        if (ctx->d_png) cudaFree(ctx->d_png);
+        ctx->d_png = NULL; ctx->d_png_cap = 0;
+        CK(cudaMalloc(&ctx->d_png, nf + 16));
+        ctx->d_png_cap = nf + 16;
+    }
+    if (ctx->d_out_cap < bound + 16) {
+        if (ctx->d_out) cudaFree(ctx->d_out);
+        ctx->d_out = NULL; ctx->d_out_cap = 0;
+        CK(cudaMalloc(&ctx->d_out, bound + 16));
+        ctx->d_out_cap = bound + 16;
+    }
+    cudaStream_t st = 0;
+    CK(cudaMemcpyAsync(ctx->d_in, pix, npix, cudaMemcpyHostToDevice, st));
+    int rc = dfl_b200_png_filter_device(ctx, ctx->d_in, row_bytes, height, (int)channels, filter_mode, ctx->d_png, st);
+    if (rc) return rc;
+    size_t body = 0;
+    uint32_t adler = 1;
+    rc = dfl_b200_deflate_device(ctx, ctx->d_png, nf, 0, 1, ctx->d_out, bound, &body, &adler, st);
+    if (rc) return rc;
+    const size_t idat = 2 + body + 4, total = 8 + 25 + 12 + idat + 12;
+    if (cap < total) return DFL_E_SZ;
+    uint8_t *p = out;
+    memcpy(p, sig, 8); p += 8;
+    put_be32(p, 13); memcpy(p + 4, "IHDR", 4);
+    put_be32(p + 8, width); put_be32(p + 12, height);
+    p[16] = 8; p[17] = ctype[channels]; p[18] = 0; p[19] = 0; p[20] = 0; /* depth, colour type, deflate, adaptive filtering, no interlace */
+    put_be32(p + 21, png_crc(p + 4, 17)); p += 25;
+    put_be32(p, (uint32_t)idat); memcpy(p + 4, "IDAT", 4);
+    p[8] = 0x78; p[9] = 0x9C;
+    CK(cudaMemcpy(p + 10, ctx->d_out, body, cudaMemcpyDeviceToHost));
+    put_be32(p + 10 + body, adler);
+    put_be32(p + 8 + idat, png_crc(p + 4, 4 + idat)); p += 12 + idat;
+    put_be32(p, 0); memcpy(p + 4, "IEND", 4); put_be32(p + 8, png_crc(p + 4, 4));
+    *out_len = total;
+    return DFL_OK;
 }

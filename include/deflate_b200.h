@@ -144,6 +144,21 @@ int dfl_b200_inflate_rounds(dfl_ctx *ctx); /* pointer-jumping rounds of the last
 int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t in_len, const uint64_t *seg_off, size_t nseg,
                              uint32_t seg_bytes, uint8_t *out, size_t n);
 
+/*
+ * PNG scanline filtering ahead of the compressor: the forward direction of the
+ * reference's defilter() (src/png/png_decoder.c:819-857; filter ids src/png/include/png_decoder.h:57-61).
+ * d_pix: rows * row_bytes unfiltered bytes; d_out: rows * (row_bytes + 1) bytes, [type | filtered row] per row.
+ * bpp = bytes per pixel.  mode 0 = per row the type with the smallest sum of |residual| (None, Sub, Up,
+ * Average, Paeth; first minimum), 1..5 = that type - 1 for every row.
+ */
+int dfl_b200_png_filter_device(dfl_ctx *ctx, const uint8_t *d_pix, size_t row_bytes, size_t rows, int bpp, int mode,
+                               uint8_t *d_out, void *stream);
+/* 8-bit grey / grey+alpha / RGB / RGBA pixels (channels 1..4, host memory) -> a PNG file (signature, IHDR, one
+ * IDAT, IEND; chunk CRCs as src/include/crc.h:22-30): filter + compress on the GPU. */
+size_t dfl_b200_png_bound(const dfl_params *prm, uint32_t width, uint32_t height, uint32_t channels);
+int dfl_b200_png_encode_host(dfl_ctx *ctx, const uint8_t *pix, uint32_t width, uint32_t height, uint32_t channels,
+                             int filter_mode, uint8_t *out, size_t cap, size_t *out_len);
+
 /* Which kernel resolves the greedy parse of a chunk: 0 = chosen by the chunk's segment count (default),
  * 1 = one warp per segment (k_parse_warp), 2 = one CTA per segment (k_parse).  Same tokens either way. */
 int dfl_b200_set_parse_mode(dfl_ctx *ctx, int mode);

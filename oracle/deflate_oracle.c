@@ -898,3 +898,61 @@ long orc_zlib_decompress(const uint8_t *in, long n, uint8_t *out, long cap)
     if (a != orc_adler32(1, out, (size_t)outn)) return -25;  /* E_ZADL32 */
     return outn;
 }
+
+/* ------------------------------------------------------------------------- */
+/* PNG scanline filtering                        */
+/* ------------------------------------------------------------------------- */
+
+/* Paeth predictor of the PNG specification (the reference's Paeth, src/png/png_decoder.c:803-817,
+ * assigns pa three times and never sets pb / pc: SURVEY 8(d) says to use the specification's). */
+static int orc_paeth(int a, int b, int c)
+{
+    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+/* The forward direction of defilter() (src/png/png_decoder.c:819-857; filter ids
+ * src/png/include/png_decoder.h:57-61).  mode 0: per row the type with the smallest sum of
+ * |residual as a signed byte| (first minimum in the order None, Sub, Up, Average, Paeth);
+ * mode 1..5: type mode - 1 for every row.  out: rows * (row_bytes + 1) bytes. */
+void orc_png_filter(const uint8_t *pix, long row_bytes, long rows, int bpp, int mode, uint8_t *out)
+{
+    long y, x;
+    for (y = 0; y < rows; y++) {
+        const uint8_t *cur = pix + y * row_bytes, *prev = y ? cur - row_bytes : NULL;
+        uint8_t *o = out + y * (row_bytes + 1);
+        unsigned long sum[5] = {0, 0, 0, 0, 0};
+        int type = mode ? mode - 1 : 0, k;
+        for (k = 0; k < 5; k++) {
+            if (mode && k != type) continue;
+            for (x = 0; x < row_bytes; x++) {
+                int v = cur[x], a = x >= bpp ? cur[x - bpp] : 0, b = prev ? prev[x] : 0, c = (prev && x >= bpp) ? prev[x - bpp] : 0;
+                int pred = k == 0 ? 0 : k == 1 ? a : k == 2 ? b : k == 3 ? (a + b) >> 1 : orc_paeth(a, b, c);
+                uint8_t r = (uint8_t)(v - pred);
+                sum[k] += r < 128 ? r : 256 - r;
+            }
+        }
+        if (!mode)
+            for (k = 1; k < 5; k++)
+                if (sum[k] < sum[type]) type = k;
+        o[0] = (uint8_t)type;
+        for (x = 0; x < row_bytes; x++) {
+            int v = cur[x], a = x >= bpp ? cur[x - bpp] : 0, b = prev ? prev[x] : 0, c = (prev && x >= bpp) ? prev[x - bpp] : 0;
+            int pred = type == 0 ? 0 : type == 1 ? a : type == 2 ? b : type == 3 ? (a + b) >> 1 : orc_paeth(a, b, c);
+            o[1 + x] = (uint8_t)(v - pred);
+        }
+    }
+}
+
+/* CRC-32 of PNG chunks (calc_crc, src/include/crc.h:22-30: reflected 0xEDB88320, init and final ~0). */
+uint32_t orc_crc32(const uint8_t *data, size_t len)
+{
+    uint32_t c = 0xFFFFFFFFu;
+    size_t n;
+    int k;
+    for (n = 0; n < len; n++) {
+        c ^= data[n];
+        for (k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+    }
+    return ~c;
+}

@@ -87,6 +87,10 @@ uint32_t orc_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);
 long orc_inflate_raw(const uint8_t *in, long n, uint8_t *out, long cap, long *consumed);
 long orc_zlib_decompress(const uint8_t *in, long n, uint8_t *out, long cap);
 
+/* PNG scanline filtering, the forward direction of defilter() (src/png/png_decoder.c:819-857), and chunk CRC. */
+void orc_png_filter(const uint8_t *pix, long row_bytes, long rows, int bpp, int mode, uint8_t *out);
+uint32_t orc_crc32(const uint8_t *data, size_t len);
+
 /* Token helpers for tests. */
 long orc_tokens_expand(const uint32_t *tokens, long ntok, const uint8_t *hist, long hist_len,
                        uint8_t *out, long cap);

@@ -75,6 +75,9 @@ def lib() -> C.CDLL:
         L.orc_bound.argtypes = [C.c_long, C.POINTER(OrcParams)]
         L.orc_zlib_compress.restype = C.c_long
         L.orc_zlib_compress.argtypes = [u8p, C.c_long, C.POINTER(OrcParams), u8p, C.c_long]
+        L.orc_png_filter.argtypes = [u8p, C.c_long, C.c_long, C.c_int, C.c_int, u8p]
+        L.orc_crc32.restype = C.c_uint32
+        L.orc_crc32.argtypes = [u8p, C.c_size_t]
         L.orc_adler32.restype = C.c_uint32
         L.orc_adler32.argtypes = [C.c_uint32, u8p, C.c_size_t]
         L.orc_adler32_combine.restype = C.c_uint32
@@ -221,3 +224,19 @@ def ref_records_to_tokens(recs: np.ndarray) -> np.ndarray:
     ll = recs[:, 4].astype(np.uint32)
     d = recs[:, 5].astype(np.uint32)
     return np.where(d == 0, ll & 0xFF, (d << 16) | ll).astype(np.uint32)
+
+
+def png_filter(img, mode: int = 0) -> np.ndarray:
+    """Filtered scanlines ([type | row] per row) of an (h, w, c) or (h, row_bytes) uint8 image."""
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    h = a.shape[0]
+    bpp = a.shape[2] if a.ndim == 3 else 1
+    row = a.size // h if h else 0
+    out = np.empty(h * (row + 1), dtype=np.uint8)
+    lib().orc_png_filter(a.ctypes.data, row, h, bpp, mode, out.ctypes.data)
+    return out
+
+
+def crc32(data) -> int:
+    a = _u8(data)
+    return int(lib().orc_crc32(a.ctypes.data, a.size))

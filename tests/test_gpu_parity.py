@@ -573,3 +573,67 @@ def test_fuzz_structured_inputs(D, O, seed):
     assert z2 == z
     assert comp.decompress(z2, comp.seg_index(), data.size) == data.tobytes()
     comp.close()
+
+
+# ---- PNG scanline filter + container ----
+
+def _img(h, w, c, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([(xx * (k + 1) // 3 + yy * (4 - k) // 2 + 40 * k) for k in range(c)], axis=-1)
+    img = img + rng.integers(-2, 3, size=img.shape)
+    img[h // 3:h // 2, w // 4:w // 2] = rng.integers(0, 256, size=img[h // 3:h // 2, w // 4:w // 2].shape)
+    return (img & 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 1), (3, 5, 3), (17, 33, 4), (300, 257, 3), (64, 4096, 3), (1000, 100, 2), (7, 5000, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def test_png_filter_matches_oracle(D, O, h, w, c, mode):
+    """k_png_filter == the oracle's forward filter, byte for byte (filter choice included)."""
+    import torch
+
+    img = _img(h, w, c, 3 * h + w + c)
+    dev = torch.device("cuda:0")
+    d_pix = torch.from_numpy(img.reshape(-1)).to(dev)
+    d_out = torch.zeros(h * (w * c + 1), dtype=torch.uint8, device=dev)
+    comp = D.Compressor()
+    comp.png_filter_device(d_pix.data_ptr(), w * c, h, c, d_out.data_ptr(), mode, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), O.png_filter(img, mode))
+    comp.close()
+
+
+def _png_chunks(png: bytes):
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, []
+    while pos < len(png):
+        n = int.from_bytes(png[pos:pos + 4], "big")
+        typ, data = png[pos + 4:pos + 8], png[pos + 8:pos + 8 + n]
+        assert int.from_bytes(png[pos + 8 + n:pos + 12 + n], "big") == (zlib.crc32(typ + data) & 0xFFFFFFFF), typ
+        chunks.append((typ, data))
+        pos += 12 + n
+    assert pos == len(png)
+    return chunks
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 1), (48, 64, 3), (33, 17, 4), (20, 50, 2), (600, 800, 3)])
+def test_png_encode_file(D, O, h, w, c):
+    """The file has the structure src/png/png_decoder.c reads (signature, IHDR, IDAT, IEND with good
+    CRCs); its IDAT is a zlib stream of exactly the oracle's filtered scanlines, and for the small images
+    un-filtering them (the reference's defilter direction) gives the pixels back."""
+    from test_oracle import _png_unfilter
+
+    img = _img(h, w, c, 11 * h + w)
+    comp = D.Compressor()
+    png = comp.png_encode(img)
+    comp.close()
+    chunks = _png_chunks(png)
+    assert [t for t, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    ihdr = chunks[0][1]
+    assert int.from_bytes(ihdr[0:4], "big") == w and int.from_bytes(ihdr[4:8], "big") == h
+    assert ihdr[8] == 8 and ihdr[9] == {1: 0, 2: 4, 3: 2, 4: 6}[c] and ihdr[10:13] == b"\x00\x00\x00"
+    filtered = np.frombuffer(zlib.decompress(chunks[1][1]), dtype=np.uint8)
+    assert np.array_equal(filtered, O.png_filter(img, 0))
+    assert D.deflate_decompress(chunks[1][1]) == filtered.tobytes()
+    if h * w <= 4096:
+        assert np.array_equal(_png_unfilter(filtered, h, w * c, c), img.reshape(h, w * c))

@@ -153,3 +153,74 @@ def test_dictionary_priming_helps_and_is_consistent(O):
     whole, stats = O.deflate_body(data, 0, data.size, O.params(), is_final=True)
     skip = sum(s.out_bytes for s in stats[:3])
     assert whole[skip:] == body
+
+
+# ---- PNG scanline filter + CRC ----
+
+def _png_unfilter(filtered: np.ndarray, h: int, row: int, bpp: int) -> np.ndarray:
+    """The reference's defilter() direction (src/png/png_decoder.c:819-857) with the specification's Paeth:
+    an independent check that the oracle's forward filter is invertible and standard."""
+    out = np.zeros((h, row), dtype=np.uint8)
+    for y in range(h):
+        t = int(filtered[y * (row + 1)])
+        f = filtered[y * (row + 1) + 1:(y + 1) * (row + 1)].astype(np.int32)
+        prev = out[y - 1].astype(np.int32) if y else np.zeros(row, dtype=np.int32)
+        cur = np.zeros(row, dtype=np.int32)
+        for x in range(row):
+            a = cur[x - bpp] if x >= bpp else 0
+            b = prev[x]
+            c = prev[x - bpp] if x >= bpp else 0
+            if t == 0:
+                p = 0
+            elif t == 1:
+                p = a
+            elif t == 2:
+                p = b
+            elif t == 3:
+                p = (a + b) >> 1
+            else:
+                pp = a + b - c
+                pa, pb, pc = abs(pp - a), abs(pp - b), abs(pp - c)
+                p = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+            cur[x] = (f[x] + p) & 255
+        out[y] = cur.astype(np.uint8)
+    return out
+
+
+def _test_image(h: int, w: int, c: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([(xx * (k + 1) // 3 + yy * (4 - k) // 2 + 40 * k) for k in range(c)], axis=-1)
+    img = img + rng.integers(-2, 3, size=img.shape)
+    img[h // 3:h // 2, w // 4:w // 2] = rng.integers(0, 256, size=img[h // 3:h // 2, w // 4:w // 2].shape)  # a noisy patch
+    return (img & 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 1), (3, 5, 3), (17, 33, 4), (40, 64, 3), (9, 100, 2), (25, 31, 1)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
+def test_png_filter_inverts(O, h, w, c, mode):
+    img = _test_image(h, w, c, 7 * h + w + c)
+    f = O.png_filter(img, mode)
+    assert f.size == h * (w * c + 1)
+    types = f[::w * c + 1]
+    assert types.max() <= 4 and (mode == 0 or (types == mode - 1).all())
+    assert np.array_equal(_png_unfilter(f, h, w * c, c), img.reshape(h, w * c))
+
+
+def test_png_filter_picks_minimum_sum(O):
+    img = _test_image(30, 50, 3, 99)
+    row = 150
+    f0 = O.png_filter(img, 0)
+    sums = []
+    for m in range(1, 6):
+        fm = O.png_filter(img, m).reshape(30, row + 1)[:, 1:].astype(np.int32)
+        sums.append(np.where(fm < 128, fm, 256 - fm).sum(axis=1))
+    sums = np.stack(sums, axis=1)
+    assert np.array_equal(f0[::row + 1], sums.argmin(axis=1).astype(np.uint8))  # argmin = first minimum
+
+
+def test_crc32_matches_zlib(O):
+    import zlib
+
+    for data in (b"", b"IEND", b"123456789", bytes(range(256)) * 9):
+        assert O.crc32(data) == (zlib.crc32(data) & 0xFFFFFFFF)
