@@ -708,20 +708,40 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                 sx_iter++; sx_walk += c1 & 0xFF; sx_fin += (c1 >> 8) & 0xFF; sx_done += c1 >> 16;
             }
 #endif
-            /* phase A: walk the bucket backwards until a candidate passes the 4-byte filter */
+            /* phase A: walk the bucket backwards until a candidate passes the 4-byte filter.  Without a chain
+             * limit two entries are fetched per step: their list and data loads overlap (the loop is bound by
+             * the dependent shared-memory latency of a hop, not by issue slots). */
             if (st == ST_WALK) {
+                if (HAS_K) {
 #pragma unroll 1
-                for (int t = 0; t < HOP_BATCH; t++) {
-                    if (k <= k_lo || (HAS_K && hops >= K)) { st = ST_DONE; break; }
-                    q = (int)lds_u16(lbase + 2 * (--k));
+                    for (int t = 0; t < HOP_BATCH; t++) {
+                        if (k <= k_lo || hops >= K) { st = ST_DONE; break; }
+                        q = (int)lds_u16(lbase + 2 * (--k));
+                        if (p - q > W) { st = ST_DONE; break; }
+                        hops++;
+                        /* filter: the 4 bytes ending at offset best_len (fmask0 while nothing is found
+                         * yet) must match for q to beat the best so far */
+                        if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < HOP_BATCH; t += 2) {
+                        if (k <= k_lo) { st = ST_DONE; break; }
+                        const int q1 = (int)lds_u16(lbase + 2 * (k - 1));
+                        const int q2 = k - 1 > k_lo ? (int)lds_u16(lbase + 2 * (k - 2)) : p - W - 1; /* no second entry: reads as "outside the window" */
+                        const uint32_t w1 = ld4s(dbase + q1 + foff), w2 = ld4s(dbase + (q2 < 0 ? 0 : q2) + foff);
 #ifdef DFL_SEARCH_STATS
-                    sx_hops++;
+                        sx_hops += 2;
 #endif
-                    if (p - q > W) { st = ST_DONE; break; }
-                    if (HAS_K) hops++;
-                    /* filter: the 4 bytes ending at offset best_len (fmask0 while nothing is found
-                     * yet) must match for q to beat the best so far */
-                    if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
+                        k--;
+                        q = q1;
+                        if (p - q1 > W) { st = ST_DONE; break; }
+                        if ((w1 & fmask) == fword) { st = ST_CAND; break; }
+                        k--;
+                        q = q2;
+                        if (p - q2 > W) { st = ST_DONE; break; }
+                        if ((w2 & fmask) == fword) { st = ST_CAND; break; }
+                    }
                 }
             }
 #ifdef DFL_SEARCH_STATS
