@@ -756,20 +756,17 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
             /* phase B: full compare (check_dup_str) for the lanes holding a candidate */
             if (st == ST_CAND) {
                 int len;
-                uint32_t x = ld4s(dbase + q) ^ pw0;
-                if (x) {
-                    len = (__ffs(x) - 1) >> 3;
+                const uint32_t x0 = ld4s(dbase + q) ^ pw0, x1 = ld4s(dbase + q + 4) ^ pw1; /* both loads in flight together */
+                if (x0) {
+                    len = (__ffs(x0) - 1) >> 3;
+                } else if (x1) {
+                    len = 4 + ((__ffs(x1) - 1) >> 3);
                 } else {
-                    x = ld4s(dbase + q + 4) ^ pw1;
-                    if (x) {
-                        len = 4 + ((__ffs(x) - 1) >> 3);
-                    } else {
-                        len = 8;
-                        while (len < maxlen) {
-                            x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
-                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                            len += 4;
-                        }
+                    len = 8;
+                    while (len < maxlen) {
+                        const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
+                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                        len += 4;
                     }
                 }
                 if (len > maxlen) len = maxlen;
@@ -861,11 +858,14 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     const uint32_t g_ = hash4(hw, ngrp, sb); /* fourth byte 0 -> first bucket of the group */
                     const int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
                     uint32_t loc = 0;
-                    for (int kk = ghi - 1 - lane; kk >= glo; kk -= 32) {
-                        const int cq = (int)lds_u16(lbase + 2 * kk);
-                        const int d = hp - cq;
-                        if ((unsigned)(d - 1) < (unsigned)W && (ld4s(dbase + cq) & 0xFFFFFFu) == hw && (uint32_t)cq + 1 > loc)
-                            loc = (uint32_t)cq + 1;
+                    for (int kk = ghi - 1 - lane; kk >= glo; kk -= 64) { /* two steps' loads in flight together */
+                        const int kb = kk - 32;
+                        const int cq = (int)lds_u16(lbase + 2 * kk), cq2 = kb >= glo ? (int)lds_u16(lbase + 2 * kb) : hp;
+                        const int d = hp - cq, d2 = hp - cq2;
+                        const bool in1 = (unsigned)(d - 1) < (unsigned)W, in2 = (unsigned)(d2 - 1) < (unsigned)W;
+                        const uint32_t t1 = in1 ? ld4s(dbase + cq) & 0xFFFFFFu : ~hw, t2 = in2 ? ld4s(dbase + cq2) & 0xFFFFFFu : ~hw;
+                        if (t1 == hw && (uint32_t)cq + 1 > loc) loc = (uint32_t)cq + 1;
+                        if (t2 == hw && (uint32_t)cq2 + 1 > loc) loc = (uint32_t)cq2 + 1;
                     }
                     loc = __reduce_max_sync(FULL, loc);
                     if (lane == L && loc) { best_len = DFL_MIN_MATCH; best_dist = p - (int)(loc - 1); }
