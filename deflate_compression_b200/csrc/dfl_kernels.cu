@@ -733,14 +733,15 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
 #ifdef DFL_SEARCH_STATS
                         sx_hops += 2;
 #endif
-                        k--;
-                        q = q1;
-                        if (p - q1 > W) { st = ST_DONE; break; }
-                        if ((w1 & fmask) == fword) { st = ST_CAND; break; }
-                        k--;
-                        q = q2;
-                        if (p - q2 > W) { st = ST_DONE; break; }
-                        if ((w2 & fmask) == fword) { st = ST_CAND; break; }
+                        const bool o1 = p - q1 > W, h1 = (w1 & fmask) == fword, o2 = p - q2 > W, h2 = (w2 & fmask) == fword;
+                        if (o1 | h1 | o2 | h2) { /* one exit; which of the four it was is sorted out off the hot path */
+                            if (o1) { st = ST_DONE; k -= 1; }
+                            else if (h1) { st = ST_CAND; q = q1; k -= 1; }
+                            else if (o2) { st = ST_DONE; k -= 2; }
+                            else { st = ST_CAND; q = q2; k -= 2; }
+                            break;
+                        }
+                        k -= 2;
                     }
                 }
             }
