@@ -674,7 +674,7 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
     if (ctx->d_png) cudaFree(ctx->d_png);
         ctx->inf_w = NULL;
         ctx->inf_cap = 0;
-        CK(cudaMalloc(&ctx->inf_w, words * sizeof(uint32_t) + 16));
+        CK(cudaMalloc(&ctx->inf_w, words * sizeof(uint32_t) + 16 + words / INF_BLK + 16)); /* + one done flag per resolve block */
         ctx->inf_cap = words;
     }
     ctx->ev_n = 0;
@@ -692,9 +692,11 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
          * segments a pointer spans, so ceil(log2(ns)) + 2 rounds always suffice */
         int max_rounds = 3;
         for (int v = ns; v > 1; v >>= 1) max_rounds++;
+        unsigned char *blk_done = reinterpret_cast<unsigned char *>(ctx->inf_w + ctx->inf_cap + 4);
+        CK(cudaMemsetAsync(blk_done, 0, (size_t)((cnt + INF_BLK - 1) / INF_BLK), st));
         for (int r = 0;; r++) {
             CK(cudaMemsetAsync(pending, 0, sizeof(unsigned int), st));
-            LAUNCH(K_INF_RESOLVE, k_inf_resolve, 148 * 16, 256, 0, st, ctx->inf_w, cnt, chunk_lo, (const uint8_t *)d_out, pending);
+            LAUNCH(K_INF_RESOLVE, k_inf_resolve, 148 * 16, 256, 0, st, ctx->inf_w, cnt, chunk_lo, (const uint8_t *)d_out, blk_done, pending);
             unsigned int left = 0;
             CK(cudaMemcpyAsync(&ctx->h_state->inf_pending, pending, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

@@ -343,32 +343,46 @@ __device__ __forceinline__ uint32_t inf_jump(const uint32_t *w, long long p, uin
     return (a & INF_KNOWN) ? a : v + a;
 }
 
+#define INF_BLK 4096 /* words per resolve block: a block whose words are all values is skipped from then on */
+
 __global__ void __launch_bounds__(256)
-k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, const uint8_t *__restrict__ d_out, unsigned int *pending)
+k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, const uint8_t *__restrict__ d_out, unsigned char *blk_done,
+              unsigned int *pending)
 {
-    unsigned int left = 0;
-    const long long quads = cnt >> 2;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < quads; g += (long long)gridDim.x * blockDim.x) {
-        uint4 v = __ldcg(reinterpret_cast<const uint4 *>(w) + g);
-        if (v.x & v.y & v.z & v.w & INF_KNOWN) continue;
-        const long long p = g << 2;
-        if (!(v.x & INF_KNOWN)) v.x = inf_jump(w, p, v.x, chunk_lo, d_out);
-        if (!(v.y & INF_KNOWN)) v.y = inf_jump(w, p + 1, v.y, chunk_lo, d_out);
-        if (!(v.z & INF_KNOWN)) v.z = inf_jump(w, p + 2, v.z, chunk_lo, d_out);
-        if (!(v.w & INF_KNOWN)) v.w = inf_jump(w, p + 3, v.w, chunk_lo, d_out);
-        reinterpret_cast<uint4 *>(w)[g] = v;
-        left |= ~(v.x & v.y & v.z & v.w) & INF_KNOWN;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (cnt & 3)) {
-        const long long p = (quads << 2) + threadIdx.x;
-        const uint32_t v = __ldcg(w + p);
-        if (!(v & INF_KNOWN)) {
-            const uint32_t nv = inf_jump(w, p, v, chunk_lo, d_out);
-            w[p] = nv;
-            left |= ~nv & INF_KNOWN;
+    const long long nblk = (cnt + INF_BLK - 1) / INF_BLK;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        if (blk_done[blk]) continue; /* uniform for the CTA */
+        unsigned int left = 0;
+        const long long p0 = blk * INF_BLK;
+        const long long pend = p0 + INF_BLK < cnt ? p0 + INF_BLK : cnt;
+        const long long quads = (pend - p0) >> 2;
+        for (long long g = threadIdx.x; g < quads; g += blockDim.x) {
+            uint4 *q4 = reinterpret_cast<uint4 *>(w + p0) + g;
+            uint4 v = __ldcg(q4);
+            if (v.x & v.y & v.z & v.w & INF_KNOWN) continue;
+            const long long p = p0 + (g << 2);
+            if (!(v.x & INF_KNOWN)) v.x = inf_jump(w, p, v.x, chunk_lo, d_out);
+            if (!(v.y & INF_KNOWN)) v.y = inf_jump(w, p + 1, v.y, chunk_lo, d_out);
+            if (!(v.z & INF_KNOWN)) v.z = inf_jump(w, p + 2, v.z, chunk_lo, d_out);
+            if (!(v.w & INF_KNOWN)) v.w = inf_jump(w, p + 3, v.w, chunk_lo, d_out);
+            *q4 = v;
+            left |= ~(v.x & v.y & v.z & v.w) & INF_KNOWN;
+        }
+        if (threadIdx.x < ((pend - p0) & 3)) { /* tail of the last block */
+            const long long p = p0 + (quads << 2) + threadIdx.x;
+            const uint32_t v = __ldcg(w + p);
+            if (!(v & INF_KNOWN)) {
+                const uint32_t nv = inf_jump(w, p, v, chunk_lo, d_out);
+                w[p] = nv;
+                left |= ~nv & INF_KNOWN;
+            }
+        }
+        const int any = __syncthreads_or((int)(left != 0));
+        if (threadIdx.x == 0) {
+            if (any) atomicOr(pending, 1u);
+            else blk_done[blk] = 1;
         }
     }
-    if (__any_sync(__activemask(), left != 0) && (threadIdx.x & 31) == 0) atomicOr(pending, 1u);
 }
 
 /* words -> bytes; Adler-32 partial sums of the segment (same bookkeeping as k_match) */
