@@ -162,9 +162,15 @@ k_parse_warp(long long n, long long seg0, int nseg, dfl_params prm, const uint32
         int lim = seglen - base < 32 ? seglen - base : 32;
         uint32_t heads = 0;
         int c = cur - base;
-        while (c < lim) {
-            heads |= 1u << c;
-            c += __shfl_sync(FULL, adv, c);
+        if (c < lim && __all_sync(FULL, adv == 1 || lane >= lim)) {
+            /* a window of literals (incompressible data): every position from c on is a head */
+            heads = (lim == 32 ? 0xFFFFFFFFu : (1u << lim) - 1u) & ~((1u << c) - 1u);
+            c = lim;
+        } else {
+            while (c < lim) {
+                heads |= 1u << c;
+                c += __shfl_sync(FULL, adv, c);
+            }
         }
         cur = base + c;
         __syncwarp();
