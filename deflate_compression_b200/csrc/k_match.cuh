@@ -19,6 +19,9 @@
 #ifndef SEARCH_WARPS
 #define SEARCH_WARPS 32  /* warps that run the chunk parsers (the index build uses all 32) */
 #endif
+#ifndef LONG_CMP_FROM
+#define LONG_CMP_FROM 16 /* bytes a lane compares alone before the warp takes a long match over */
+#endif
 #ifndef SKIP_OVERRUN
 #define SKIP_OVERRUN 1   /* a chunk some chain has already entered is not started on its own */
 #endif
@@ -456,7 +459,7 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
      * chunks from the shared counter keep the warps' lanes occupied (the SM is issue bound: what counts
      * is useful lanes per instruction, not resident warps). */
     if (warp < SEARCH_WARPS) {
-        enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6 };
+        enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6, ST_LONG = 7 };
         const int W = prm.window, K = HAS_K ? prm.chain_limit : 0;
         const uint32_t ngrp = HASH_SIZE >> sb;
         /* first filter of a walk: 4 bytes when the buckets are split (the walk only looks for matches
@@ -554,7 +557,22 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                 if (HAS_K && K - hops < rem) rem = K - hops;
                 if (rem > COOP_MIN) st = ST_HEAVY;
             }
-            /* phase B: full compare (check_dup_str) for the lanes holding a candidate */
+            /* phase B: full compare (check_dup_str) for the lanes holding a candidate.  A lane compares up
+             * to LONG_CMP_FROM bytes on its own; a match still running then (logs, runs, images: up to 258
+             * bytes = 64 dependent steps for one lane) is finished by the whole warp, 128 bytes per step. */
+#define APPLY_LEN(len_)                                                                               \
+            do {                                                                                      \
+                int l_ = (len_);                                                                      \
+                if (l_ > maxlen) l_ = maxlen;                                                         \
+                st = ST_WALK;                                                                         \
+                if (l_ > best_len) {                                                                  \
+                    best_len = l_;                                                                    \
+                    best_dist = p - q;                                                                \
+                    if (l_ == maxlen) st = ST_DONE;                                                   \
+                    else { foff = l_ - 3; fmask = 0xFFFFFFFFu; fword = ld4s(dbase + p + foff); }      \
+                }                                                                                     \
+            } while (0)
+            int long_from = 0;
             if (st == ST_CAND) {
                 int len;
                 const uint32_t x0 = ld4s(dbase + q) ^ pw0, x1 = ld4s(dbase + q + 4) ^ pw1; /* both loads in flight together */
@@ -564,28 +582,49 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
                     len = 4 + ((__ffs(x1) - 1) >> 3);
                 } else {
                     len = 8;
-                    while (len < maxlen) {
+                    while (len < maxlen && len < LONG_CMP_FROM) {
                         const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
-                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                        if (x) { len += (__ffs(x) - 1) >> 3; long_from = -1; break; }
                         len += 4;
                     }
+                    if (long_from == 0 && len < maxlen) long_from = len; /* still equal at LONG_CMP_FROM bytes */
+                    else long_from = 0;
                 }
-                if (len > maxlen) len = maxlen;
-                st = ST_WALK;
-                if (len > best_len) {
-                    best_len = len;
-                    best_dist = p - q;
-                    if (len == maxlen) st = ST_DONE;
-                    else { foff = len - 3; fmask = 0xFFFFFFFFu; fword = ld4s(dbase + p + foff); }
-                }
+                if (long_from) st = ST_LONG;
+                else APPLY_LEN(len);
             }
             /* phase C: finished heads emit their token and move on; idle lanes take new
              * chunks.  One warp reduction per round steers it (votes and shuffles share a
              * slow unit on this chip). */
             const uint32_t census = __reduce_add_sync(FULL, (st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) |
-                                                                (st == ST_HEAVY ? 0x10000u : 0u));
-            const int n_busy = census & 0xFF, n_fin = (census >> 8) & 0xFF, n_heavy = census >> 16;
+                                                                (st == ST_HEAVY ? 0x10000u : 0u) | (st == ST_LONG ? 0x1000000u : 0u));
+            const int n_busy = census & 0xFF, n_fin = (census >> 8) & 0xFF, n_heavy = (census >> 16) & 0xFF, n_long = census >> 24;
             if (n_fin == 32) break;
+            if (n_long)
+            {
+                uint32_t lng = __ballot_sync(FULL, st == ST_LONG);
+                while (lng) {
+                    const int L = __ffs(lng) - 1;
+                    lng &= lng - 1;
+                    const int hp = __shfl_sync(FULL, p, L), hq = __shfl_sync(FULL, q, L), hmax = __shfl_sync(FULL, maxlen, L);
+                    const int l0 = __shfl_sync(FULL, long_from, L);
+                    int flen = hmax;
+                    for (int base = l0; base < hmax; base += 128) {
+                        const int off_ = base + 4 * lane;
+                        const uint32_t x = off_ < hmax ? ld4s(dbase + hp + off_) ^ ld4s(dbase + hq + off_) : 1u; /* the end reads as a mismatch */
+                        const uint32_t m = __ballot_sync(FULL, x != 0);
+                        if (m) {
+                            const int f = __ffs(m) - 1;
+                            const uint32_t xf = __shfl_sync(FULL, x, f);
+                            const int fo = base + 4 * f;
+                            flen = fo < hmax ? fo + ((__ffs(xf) - 1) >> 3) : hmax;
+                            break;
+                        }
+                    }
+                    if (lane == L) APPLY_LEN(flen);
+                }
+            }
+#undef APPLY_LEN
             if (n_heavy) {
                 /* cooperative walk: the 32 lanes take 32 consecutive bucket entries per pass,
                  * nearest first; one warp reduction per pass picks the longest (then nearest)

@@ -16,7 +16,7 @@ def run(data, **prm):
     return best, ph["build"] / nseg, ph["search"] / nseg, ph["plain_segments"] / nseg
 n = 64 << 20
 res = []
-for name, data, prm in (("text", synth.markov(n, 2), {}), ("text_k16", synth.markov(n, 2), dict(chain_limit=16)), ("log", synth.log(n, 3), {}), ("png", synth.png_rows(n, 6), {}), ("rand", synth.random_bytes(n, 4), {})):
+for name, data, prm in (("text", synth.markov(n, 2), {}), ("text_k16", synth.markov(n, 2), dict(chain_limit=16)), ("log", synth.log(n, 3), {}), ("png", synth.png_rows(n, 6), {}), ("rand", synth.random_bytes(n, 4), {}), ("zeros", np.zeros(n, dtype=np.uint8), {})):
     ms, b, s, pl = run(data, **prm)
     res.append(f"{name}: {ms:6.2f} ms (build {b/1e3:4.0f}K search {s/1e3:5.0f}K plain {pl:.2f})")
 print(" | ".join(res))
