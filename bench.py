@@ -11,8 +11,10 @@ text (BASELINE.json configs[1]: 256 MiB per GPU, dynamic Huffman blocks), with
 the inputs already resident in HBM.  `e2e` is the same metric through the host
 API (dfl_b200_compress_host: pinned host buffers, H2D + D2H inside the timed
 region).  For N > 1 the input shards contiguously (weak scaling: 256 MiB per
-rank, each shard primed with the preceding 32 KiB) and the step ends with the
-NCCL gather of sizes and compressed bytes to rank 0.
+rank, each shard primed with the preceding 32 KiB) and every step gathers sizes
+and compressed bytes to rank 0 with NCCL; the transfer of step k runs while the
+kernels of step k + 1 do (two output buffers), and the clock stops only after the
+last step's bytes have arrived.
 
 `--impl reference` times the reference's own CPU implementation of the path
 (oracle/_ref/libref.so, the unmodified reference LZ77 loop, on independent
@@ -221,17 +223,30 @@ def run_gpu(args) -> None:
     comp = D.Compressor(device=local)
     comp.enable_timing(True)
     cap = comp.bound(n)
-    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    # two output buffers: the gather of step k (NCCL, its own stream) overlaps the kernels of step k + 1
+    d_outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2 if world > 1 else 1)]
+    d_out = d_outs[0]
     stream = torch.cuda.current_stream().cuda_stream
     is_final = rank == world - 1
 
-    gather_buf = None
+    gather_bufs = None
     if world > 1 and rank == 0:
-        gather_buf = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+        gather_bufs = [torch.empty(world * cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+    pending = [None, None]
 
-    def step(with_gather: bool = True):
-        """One pass of the hot path over the shard (+ gather of sizes and bytes to rank 0)."""
-        comp.enqueue(d_in, n, hist, is_final, d_out.data_ptr(), cap, stream)
+    def drain(b=None):
+        for k in ((0, 1) if b is None else (b,)):
+            if pending[k] is not None:
+                for q in pending[k]:
+                    q.wait()
+                pending[k] = None
+
+    def step(i: int = 0, with_gather: bool = True):
+        """One pass of the hot path over the shard (+ gather of sizes and bytes to rank 0; the transfer
+        itself is left in flight and is waited for before its buffers are used again, or by drain())."""
+        b = i & 1 if world > 1 else 0
+        drain(b)
+        comp.enqueue(d_in, n, hist, is_final, d_outs[b].data_ptr(), cap, stream)
         out_len, adler = comp.finish(stream)
         if world > 1 and with_gather:
             sizes = torch.zeros(world, dtype=torch.int64, device=dev)
@@ -240,13 +255,12 @@ def run_gpu(args) -> None:
             sz = sizes.tolist()
             if rank == 0:
                 offs = np.concatenate([[0], np.cumsum(sz)])
-                gather_buf[:sz[0]].copy_(d_out[:sz[0]])
-                ops = [dist.P2POp(dist.irecv, gather_buf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
-                for q in dist.batch_isend_irecv(ops):
-                    q.wait()
+                gbuf = gather_bufs[b]
+                gbuf[:sz[0]].copy_(d_outs[b][:sz[0]])
+                ops = [dist.P2POp(dist.irecv, gbuf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
+                pending[b] = dist.batch_isend_irecv(ops)
             else:
-                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, d_out[:out_len], 0)]):
-                    q.wait()
+                pending[b] = dist.batch_isend_irecv([dist.P2POp(dist.isend, d_outs[b][:out_len], 0)])
         return out_len, adler
 
     def sync():
@@ -255,8 +269,9 @@ def run_gpu(args) -> None:
         torch.cuda.synchronize()
 
     # ---- device-timed throughput ----
-    for _ in range(args.warmup):
-        out_len, adler = step()
+    for k in range(args.warmup):
+        out_len, adler = step(k)
+    drain()
     launches0 = comp.kernel_launches()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -267,9 +282,10 @@ def run_gpu(args) -> None:
     k_match_ms = []
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        out_len, adler = step()
+    for k in range(args.steps):
+        out_len, adler = step(k)
         k_match_ms.append(comp.kernel_ms()["k_match"])
+    drain()  # every step's bytes have arrived on rank 0 before the clock stops
     e1.record()
     sync()
     t1 = time.perf_counter()
@@ -282,8 +298,8 @@ def run_gpu(args) -> None:
     if world > 1:
         sync()
         e0.record()
-        for _ in range(args.steps):
-            step(with_gather=False)
+        for k in range(args.steps):
+            step(k, with_gather=False)
         e1.record()
         sync()
         ms_nogather = e0.elapsed_time(e1)
@@ -304,7 +320,7 @@ def run_gpu(args) -> None:
 
     # ---- the way back: segment-parallel inflate of what the timed step wrote, device to
     # device, compared with the shard on the device.  Not part of `value`; reported beside it. ----
-    out_len, adler = step(with_gather=False)
+    out_len, adler = step(0, with_gather=False)
     d_off = torch.from_numpy(comp.seg_index().astype(np.int64)).to(dev)
     d_back = torch.zeros(hist + n, dtype=torch.uint8, device=dev)
     d_back[:hist].copy_(d_buf[:hist])
