@@ -151,6 +151,18 @@ static void free_ws(dfl_ctx *ctx)
     ctx->ws_segs = 0;
 }
 
+/* grow-only device buffer of the context */
+static int grow_dev(dfl_ctx *ctx, uint8_t **buf, size_t *cap, size_t need)
+{
+    if (*cap >= need) return DFL_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = NULL;
+    *cap = 0;
+    CK(cudaMalloc(buf, need));
+    *cap = need;
+    return DFL_OK;
+}
+
 static int ensure_index(dfl_ctx *ctx, size_t nseg)
 {
     if (ctx->seg_index_cap < nseg + 1) {
@@ -488,18 +500,8 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
     CK(cudaSetDevice(ctx->device));
     const dfl_params prm = ctx->prm;
     size_t bound = dfl_b200_bound(&prm, n);
-    if (ctx->d_in_cap < n + 16) {
-        if (ctx->d_in) cudaFree(ctx->d_in);
-        ctx->d_in = NULL; ctx->d_in_cap = 0;
-        CK(cudaMalloc(&ctx->d_in, n + 16));
-        ctx->d_in_cap = n + 16;
-    }
-    if (ctx->d_out_cap < bound + 16) {
-        if (ctx->d_out) cudaFree(ctx->d_out);
-        ctx->d_out = NULL; ctx->d_out_cap = 0;
-        CK(cudaMalloc(&ctx->d_out, bound + 16));
-        ctx->d_out_cap = bound + 16;
-    }
+    { const int rc_ = grow_dev(ctx, &ctx->d_in, &ctx->d_in_cap, n + 16); if (rc_) return rc_; }
+    { const int rc_ = grow_dev(ctx, &ctx->d_out, &ctx->d_out_cap, bound + 16); if (rc_) return rc_; }
     uint8_t *d_body = ctx->d_out + 2; /* body at +2 so the zlib header can be prepended without a second copy */
     size_t body = 0;
     uint32_t adler = 1;
@@ -737,18 +739,8 @@ extern "C" int dfl_b200_decompress_host(dfl_ctx *ctx, const uint8_t *in, size_t 
     if ((in[0] & 0x0F) != 8 || (in[0] >> 4) > 7 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return DFL_E_DATA;
     CK(cudaSetDevice(ctx->device));
     const size_t body_len = in_len - 6;
-    if (ctx->d_in_cap < in_len + 16) {
-        if (ctx->d_in) cudaFree(ctx->d_in);
-        ctx->d_in = NULL; ctx->d_in_cap = 0;
-        CK(cudaMalloc(&ctx->d_in, in_len + 16));
-        ctx->d_in_cap = in_len + 16;
-    }
-    if (ctx->d_out_cap < n + 16) {
-        if (ctx->d_out) cudaFree(ctx->d_out);
-        ctx->d_out = NULL; ctx->d_out_cap = 0;
-        CK(cudaMalloc(&ctx->d_out, n + 16));
-        ctx->d_out_cap = n + 16;
-    }
+    { const int rc_ = grow_dev(ctx, &ctx->d_in, &ctx->d_in_cap, in_len + 16); if (rc_) return rc_; }
+    { const int rc_ = grow_dev(ctx, &ctx->d_out, &ctx->d_out_cap, n + 16); if (rc_) return rc_; }
     uint64_t *d_off = NULL;
     CK(cudaMalloc(&d_off, (nseg + 1) * sizeof(uint64_t)));
     cudaStream_t st = 0;
@@ -838,24 +830,9 @@ extern "C" int dfl_b200_png_encode_host(dfl_ctx *ctx, const uint8_t *pix, uint32
     const dfl_params prm = ctx->prm;
     const size_t bound = dfl_b200_bound(&prm, nf);
     if (cap < 8 + 25 + 12 + 12) return DFL_E_SZ;
-    if (ctx->d_in_cap < npix + 16) {
-        if (ctx->d_in) cudaFree(ctx->d_in);
-        ctx->d_in = NULL; ctx->d_in_cap = 0;
-        CK(cudaMalloc(&ctx->d_in, npix + 16));
-        ctx->d_in_cap = npix + 16;
-    }
-    if (ctx->d_png_cap < nf + 16) {
-        if (ctx->d_png) cudaFree(ctx->d_png);
-        ctx->d_png = NULL; ctx->d_png_cap = 0;
-        CK(cudaMalloc(&ctx->d_png, nf + 16));
-        ctx->d_png_cap = nf + 16;
-    }
-    if (ctx->d_out_cap < bound + 16) {
-        if (ctx->d_out) cudaFree(ctx->d_out);
-        ctx->d_out = NULL; ctx->d_out_cap = 0;
-        CK(cudaMalloc(&ctx->d_out, bound + 16));
-        ctx->d_out_cap = bound + 16;
-    }
+    { const int rc_ = grow_dev(ctx, &ctx->d_in, &ctx->d_in_cap, npix + 16); if (rc_) return rc_; }
+    { const int rc_ = grow_dev(ctx, &ctx->d_png, &ctx->d_png_cap, nf + 16); if (rc_) return rc_; }
+    { const int rc_ = grow_dev(ctx, &ctx->d_out, &ctx->d_out_cap, bound + 16); if (rc_) return rc_; }
     cudaStream_t st = 0;
     CK(cudaMemcpyAsync(ctx->d_in, pix, npix, cudaMemcpyHostToDevice, st));
     int rc = dfl_b200_png_filter_device(ctx, ctx->d_in, row_bytes, height, (int)channels, filter_mode, ctx->d_png, st);
