@@ -106,7 +106,24 @@ k_emit(const uint8_t *__restrict__ d_in, long long n, long long seg0, long long 
                 q[1] = (uint8_t)len; q[2] = (uint8_t)(len >> 8);
                 q[3] = (uint8_t)~len; q[4] = (uint8_t)(~len >> 8);
             }
-            for (long long i = tid; i < len; i += EMIT_THREADS) q[5 + i] = src[o + i];
+            /* copy: whole 32-bit words of the destination, each assembled from the two source words that
+             * cover it; the unaligned head and tail byte by byte */
+            {
+                uint8_t *d0 = q + 5;
+                const uint8_t *s0 = src + o;
+                long long head = (long long)((4 - ((uintptr_t)d0 & 3)) & 3);
+                if (head > len) head = len;
+                const long long nw = (len - head) >> 2;
+                if (tid < head) d0[tid] = s0[tid];
+                const uint8_t *sw = s0 + head;                     /* source of the first whole word */
+                const int sh = (int)((uintptr_t)sw & 3) * 8;
+                const uint32_t *sa = reinterpret_cast<const uint32_t *>(sw - ((uintptr_t)sw & 3));
+                uint32_t *da = reinterpret_cast<uint32_t *>(d0 + head);
+                /* the second source word is only read when the shift needs it: never past the segment's bytes */
+                for (long long w = tid; w < nw; w += EMIT_THREADS)
+                    da[w] = sh ? __funnelshift_r(__ldg(sa + w), __ldg(sa + w + 1), sh) : __ldg(sa + w);
+                for (long long i = head + 4 * nw + tid; i < len; i += EMIT_THREADS) d0[i] = s0[i];
+            }
         }
         if (tid == 0) {
             uint8_t *q = dst + seglen + 5 * nst;
