@@ -673,10 +673,11 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
     const size_t words = chunk_segs * seg_bytes;
     if (ctx->inf_cap < words) {
         if (ctx->inf_w) cudaFree(ctx->inf_w);
-    if (ctx->d_png) cudaFree(ctx->d_png);
         ctx->inf_w = NULL;
         ctx->inf_cap = 0;
-        CK(cudaMalloc(&ctx->inf_w, words * sizeof(uint32_t) + 16 + words / INF_BLK + 16)); /* + one done flag per resolve block */
+        const size_t inf_bytes = words * sizeof(uint32_t) + 16 + words / INF_BLK + 16; /* + one done flag per resolve block */
+        CK(cudaMalloc(&ctx->inf_w, inf_bytes));
+        CK(cudaMemsetAsync(ctx->inf_w, 0x80, inf_bytes, st)); /* every word starts as a value, never as a pointer */
         ctx->inf_cap = words;
     }
     ctx->ev_n = 0;
@@ -698,7 +699,8 @@ extern "C" int dfl_b200_inflate_device(dfl_ctx *ctx, const uint8_t *d_body, size
         CK(cudaMemsetAsync(blk_done, 0, (size_t)((cnt + INF_BLK - 1) / INF_BLK), st));
         for (int r = 0;; r++) {
             CK(cudaMemsetAsync(pending, 0, sizeof(unsigned int), st));
-            LAUNCH(K_INF_RESOLVE, k_inf_resolve, 148 * 16, 256, 0, st, ctx->inf_w, cnt, chunk_lo, (const uint8_t *)d_out, blk_done, pending);
+            LAUNCH(K_INF_RESOLVE, k_inf_resolve, 148 * 16, 256, 0, st, ctx->inf_w, cnt, chunk_lo, (long long)hist_len,
+                   (const uint8_t *)d_out, blk_done, pending, &ctx->state->error);
             unsigned int left = 0;
             CK(cudaMemcpyAsync(&ctx->h_state->inf_pending, pending, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

@@ -330,14 +330,26 @@ k_inflate(const uint8_t *__restrict__ body, unsigned long long body_len, const u
         if (bfinal || bp >= seg_end) break;
     }
     if (!err && pos != seglen) err = 1;
-    if (err && lane == 0) atomicExch(&state->error, 2u);
+    if (err) {
+        /* a corrupt segment leaves no stale word behind: everything it did not decode reads as a value, so
+         * that k_inf_resolve never follows a "distance" this kernel did not validate */
+        pos = __shfl_sync(FULL, pos, 0);
+        if (pos < 0) pos = 0;
+        for (int t = pos + lane; t < seglen; t += 32) out[t] = INF_KNOWN;
+        if (lane == 0) atomicExch(&state->error, 2u);
+    }
 }
 
 /* One round of pointer jumping over the cnt words of a chunk (chunk position 0 = output byte chunk_lo).
  * Four words per thread and step; groups that are already all values cost one 16-byte read. */
-__device__ __forceinline__ uint32_t inf_jump(const uint32_t *w, long long p, uint32_t v, long long chunk_lo, const uint8_t *d_out)
+__device__ __forceinline__ uint32_t inf_jump(const uint32_t *w, long long p, uint32_t v, long long chunk_lo, long long q_min,
+                                             const uint8_t *d_out, unsigned int *error)
 {
     const long long q = p - (long long)v;
+    if (q < q_min) { /* before the history the caller supplied: not a word k_inflate wrote */
+        atomicExch(error, 2u);
+        return INF_KNOWN;
+    }
     if (q < 0) return INF_KNOWN | d_out[chunk_lo + q]; /* an earlier chunk (or the caller's history): final bytes */
     const uint32_t a = __ldcg(w + q);
     return (a & INF_KNOWN) ? a : v + a;
@@ -346,9 +358,10 @@ __device__ __forceinline__ uint32_t inf_jump(const uint32_t *w, long long p, uin
 #define INF_BLK 4096 /* words per resolve block: a block whose words are all values is skipped from then on */
 
 __global__ void __launch_bounds__(256)
-k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, const uint8_t *__restrict__ d_out, unsigned char *blk_done,
-              unsigned int *pending)
+k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, long long hist_len, const uint8_t *__restrict__ d_out,
+              unsigned char *blk_done, unsigned int *pending, unsigned int *error)
 {
+    const long long q_min = -(chunk_lo + hist_len); /* chunk position of the first byte that exists */
     const long long nblk = (cnt + INF_BLK - 1) / INF_BLK;
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         if (blk_done[blk]) continue; /* uniform for the CTA */
@@ -361,10 +374,10 @@ k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, const uint8_t *__r
             uint4 v = __ldcg(q4);
             if (v.x & v.y & v.z & v.w & INF_KNOWN) continue;
             const long long p = p0 + (g << 2);
-            if (!(v.x & INF_KNOWN)) v.x = inf_jump(w, p, v.x, chunk_lo, d_out);
-            if (!(v.y & INF_KNOWN)) v.y = inf_jump(w, p + 1, v.y, chunk_lo, d_out);
-            if (!(v.z & INF_KNOWN)) v.z = inf_jump(w, p + 2, v.z, chunk_lo, d_out);
-            if (!(v.w & INF_KNOWN)) v.w = inf_jump(w, p + 3, v.w, chunk_lo, d_out);
+            if (!(v.x & INF_KNOWN)) v.x = inf_jump(w, p, v.x, chunk_lo, q_min, d_out, error);
+            if (!(v.y & INF_KNOWN)) v.y = inf_jump(w, p + 1, v.y, chunk_lo, q_min, d_out, error);
+            if (!(v.z & INF_KNOWN)) v.z = inf_jump(w, p + 2, v.z, chunk_lo, q_min, d_out, error);
+            if (!(v.w & INF_KNOWN)) v.w = inf_jump(w, p + 3, v.w, chunk_lo, q_min, d_out, error);
             *q4 = v;
             left |= ~(v.x & v.y & v.z & v.w) & INF_KNOWN;
         }
@@ -372,7 +385,7 @@ k_inf_resolve(uint32_t *w, long long cnt, long long chunk_lo, const uint8_t *__r
             const long long p = p0 + (quads << 2) + threadIdx.x;
             const uint32_t v = __ldcg(w + p);
             if (!(v & INF_KNOWN)) {
-                const uint32_t nv = inf_jump(w, p, v, chunk_lo, d_out);
+                const uint32_t nv = inf_jump(w, p, v, chunk_lo, q_min, d_out, error);
                 w[p] = nv;
                 left |= ~nv & INF_KNOWN;
             }

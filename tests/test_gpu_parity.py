@@ -637,3 +637,49 @@ def test_png_encode_file(D, O, h, w, c):
     assert D.deflate_decompress(chunks[1][1]) == filtered.tobytes()
     if h * w <= 4096:
         assert np.array_equal(_png_unfilter(filtered, h, w * c, c), img.reshape(h, w * c))
+
+
+def test_png_then_inflate_then_png_one_context(D, O):
+    """One context: png_encode, then a decompress that has to grow the inflate workspace, then png_encode again.
+    (Round 1 freed the PNG scanline buffer inside the inflate grow branch and kept the dangling pointer.)"""
+    img = _img(300, 400, 3, 77)
+    comp = D.Compressor()
+    png1 = comp.png_encode(img)
+    data = make_input("markov", 61, 0, 3 * 1000 * 1000)  # more words than anything this context inflated before
+    z = comp.compress(data)
+    off = comp.seg_index()
+    assert comp.decompress(z, off, data.size) == data.tobytes()
+    png2 = comp.png_encode(img)
+    assert png1 == png2
+    filtered = np.frombuffer(zlib.decompress(_png_chunks(png2)[1][1]), dtype=np.uint8)
+    assert np.array_equal(filtered, O.png_filter(img, 0))
+    big = _img(900, 1200, 3, 78)  # grows the scanline buffer after the inflate
+    png3 = comp.png_encode(big)
+    assert np.array_equal(np.frombuffer(zlib.decompress(_png_chunks(png3)[1][1]), dtype=np.uint8), O.png_filter(big, 0))
+    comp.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gpu_inflate_corrupt_streams_fail_cleanly(D, seed):
+    """Corrupt bodies and wrong indexes end in DflError (never a fault): every word a corrupt segment did not
+    decode reads as a value, and the resolve rounds refuse distances that reach before the history."""
+    rng = np.random.default_rng(1000 + seed)
+    comp = D.Compressor()
+    data = np.concatenate([make_input("markov", 70 + seed, 0, 300000), make_input("log", 80 + seed, 0, 200000)])
+    z = comp.compress(data)
+    off = comp.seg_index()
+    for _ in range(4):
+        bad = bytearray(z)
+        for _k in range(int(rng.integers(1, 6))):
+            bad[int(rng.integers(2, len(bad) - 4))] ^= int(rng.integers(1, 256))
+        try:
+            back = comp.decompress(bytes(bad), off, data.size)
+            assert back != data.tobytes() or bytes(bad) == z
+        except D.DflError:
+            pass
+        bad_off = off.copy()
+        bad_off[int(rng.integers(1, off.size - 1))] += int(rng.integers(1, 40))
+        with pytest.raises(D.DflError):
+            comp.decompress(z, bad_off, data.size)
+    assert comp.decompress(z, off, data.size) == data.tobytes()  # the context survives all of it
+    comp.close()
