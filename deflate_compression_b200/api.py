@@ -45,6 +45,9 @@ class DflSegInfo(C.Structure):
         ("block_bits", C.c_int64),
         ("out_bytes", C.c_int64),
         ("out_offset", C.c_int64),
+        ("tree_bits", C.c_int64),
+        ("ll_bits", C.c_int64),
+        ("d_bits", C.c_int64),
     ]
 
 
@@ -102,6 +105,7 @@ def lib() -> C.CDLL:
         L.dfl_b200_seg_info.argtypes = [vp, C.c_long, C.POINTER(DflSegInfo)]
         L.dfl_b200_tokens.restype = C.c_long
         L.dfl_b200_tokens.argtypes = [vp, C.c_long, vp, C.c_long]
+        L.dfl_b200_set_match_mode.argtypes = [vp, C.c_int]
         L.dfl_b200_kernel_launches.restype = C.c_long
         L.dfl_b200_kernel_launches.argtypes = [vp]
         L.dfl_b200_enable_timing.argtypes = [vp, C.c_int]
@@ -272,6 +276,12 @@ class Compressor:
         if rc:
             raise DflError(rc, "dfl_b200_set_parse_mode")
 
+    def set_match_mode(self, mode: int) -> None:
+        """0 = k_match_run where the geometry is the default one, 1 = always k_match (same tokens)."""
+        rc = lib().dfl_b200_set_match_mode(self._ctx, int(mode))
+        if rc:
+            raise DflError(rc, "dfl_b200_set_match_mode")
+
     def num_segments(self) -> int:
         return int(lib().dfl_b200_num_segments(self._ctx))
 
@@ -302,7 +312,10 @@ class Compressor:
     def phase_cycles(self) -> dict:
         names = ("stage_in", "build", "search", "total", "sort1", "park", "sort2", "offsets", "s1_count", "s1_scan", "s1_scatter", "d11",
                  "sx_iter", "sx_walk", "sx_fin", "sx_done", "sx_cand", "sx_heads", "sx_hops", "sx_seek", "plain_segments", "warp_end_avg", "warp_end_max")
-        return {nm: int(lib().dfl_b200_phase_cycles(self._ctx, k)) for k, nm in enumerate(names)}
+        d = {nm: int(lib().dfl_b200_phase_cycles(self._ctx, k)) for k, nm in enumerate(names)}
+        if not d["total"]:  # k_match_run accumulates the three phases only
+            d["total"] = d["stage_in"] + d["build"] + d["search"]
+        return d
 
     def sort_fallbacks(self) -> int:
         return int(lib().dfl_b200_sort_fallbacks(self._ctx))

@@ -43,6 +43,7 @@ struct SegArrays {
     uint32_t *hdr_bits;  /* [nseg] */
     uint32_t *btype;     /* [nseg] */
     uint32_t *out_bytes; /* [nseg] */
+    uint32_t *cost;      /* [nseg][2]: bits of the chosen block's code description, bits of its distance symbols + extra bits */
     unsigned long long *block_bits; /* [nseg] */
     unsigned long long *out_off;    /* [nseg] */
 };

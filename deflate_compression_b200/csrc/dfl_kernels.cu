@@ -31,6 +31,7 @@
 
 #include "dfl_common.cuh"
 #include "k_match.cuh"
+#include "k_match_run.cuh"
 #include "k_parse.cuh"
 #include "k_huff.cuh"
 #include "k_emit.cuh"
@@ -61,6 +62,8 @@ struct dfl_ctx {
     unsigned long long *h_totals;     /* pinned: end offset of every piece */
     int pipe_cap;
     int parse_mode; /* 0 = by segment count, 1 = k_parse_warp, 2 = k_parse */
+    int match_mode; /* 0 = k_match_run where the geometry allows, 1 = always k_match */
+    int num_sms;
     /* segment index of the last compress call (byte offset of every segment in the body, + the end) and inflate state */
     unsigned long long *seg_index;
     size_t seg_index_cap, seg_index_n;
@@ -78,7 +81,7 @@ struct dfl_ctx {
     uint32_t *h_tokens;
     size_t h_tokens_cap;
     long nseg_kept;
-    uint32_t *h_ntok, *h_btype, *h_out_bytes;
+    uint32_t *h_ntok, *h_btype, *h_out_bytes, *h_cost;
     unsigned long long *h_block_bits, *h_out_off;
     size_t h_seg_cap;
     /* timing */
@@ -183,7 +186,7 @@ static int ensure_ws(dfl_ctx *ctx, size_t nseg_chunk)
     size_t ns = nseg_chunk;
     CK(cudaMalloc(&ctx->tokcand, ns * ctx->prm.seg_bytes * sizeof(uint32_t)));
     CK(cudaMalloc(&ctx->tokens, ns * ctx->prm.seg_bytes * sizeof(uint32_t)));
-    size_t per = (LLS + DS + LLS + DS + HDR_WORDS + 6) * sizeof(uint32_t) + 2 * sizeof(unsigned long long);
+    size_t per = (LLS + DS + LLS + DS + HDR_WORDS + 8) * sizeof(uint32_t) + 2 * sizeof(unsigned long long);
     CK(cudaMalloc(&ctx->seg_blob, ns * per + 256));
     unsigned char *p = (unsigned char *)ctx->seg_blob;
     SegArrays &A = ctx->A;
@@ -199,6 +202,7 @@ static int ensure_ws(dfl_ctx *ctx, size_t nseg_chunk)
     A.hdr_bits = (uint32_t *)p; p += ns * 4;
     A.btype = (uint32_t *)p; p += ns * 4;
     A.out_bytes = (uint32_t *)p; p += ns * 4;
+    A.cost = (uint32_t *)p; p += ns * 8;
     ctx->ws_segs = ns;
     ctx->ws_seg_bytes = ctx->prm.seg_bytes;
     return DFL_OK;
@@ -226,13 +230,15 @@ extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
     }
     if (cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_match_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MatchSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParseSmem)) != cudaSuccess ||
         cudaMalloc(&ctx->state, sizeof(DevState)) != cudaSuccess ||
-        cudaMalloc(&ctx->scratch, (size_t)SCRATCH_SLOTS * NPOS_MAX * sizeof(uint16_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->scratch, (size_t)SCRATCH_SLOTS * SCRATCH_STRIDE * sizeof(uint16_t)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_state, sizeof(DevState)) != cudaSuccess) {
         free(ctx);
         return DFL_E_CUDA;
     }
+    ctx->num_sms = prop.multiProcessorCount < SCRATCH_SLOTS ? prop.multiProcessorCount : SCRATCH_SLOTS;
     *out = ctx;
     return DFL_OK;
 }
@@ -255,7 +261,7 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     free(ctx->e_in); free(ctx->e_done);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     if (ctx->s_in) { cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_run); cudaStreamDestroy(ctx->s_out); }
-    free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_block_bits); free(ctx->h_out_off);
+    free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_cost); free(ctx->h_block_bits); free(ctx->h_out_off);
     for (int i = 0; i < ctx->ev_cap; i++) cudaEventDestroy(ctx->ev[i]);
     free(ctx->ev); free(ctx->ev_class);
     free(ctx);
@@ -274,6 +280,13 @@ extern "C" int dfl_b200_set_parse_mode(dfl_ctx *ctx, int mode)
 {
     if (!ctx || mode < 0 || mode > 2) return DFL_E_INVAL;
     ctx->parse_mode = mode;
+    return DFL_OK;
+}
+
+extern "C" int dfl_b200_set_match_mode(dfl_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 1) return DFL_E_INVAL;
+    ctx->match_mode = mode;
     return DFL_OK;
 }
 
@@ -335,13 +348,14 @@ static int keep_reserve(dfl_ctx *ctx, size_t n, size_t nseg)
         ctx->h_tokens_cap = n;
     }
     if (ctx->h_seg_cap < nseg) {
-        free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_block_bits); free(ctx->h_out_off);
+        free(ctx->h_ntok); free(ctx->h_btype); free(ctx->h_out_bytes); free(ctx->h_cost); free(ctx->h_block_bits); free(ctx->h_out_off);
         ctx->h_ntok = (uint32_t *)malloc(nseg * 4);
+        ctx->h_cost = (uint32_t *)malloc(nseg * 8);
         ctx->h_btype = (uint32_t *)malloc(nseg * 4);
         ctx->h_out_bytes = (uint32_t *)malloc(nseg * 4);
         ctx->h_block_bits = (unsigned long long *)malloc(nseg * 8);
         ctx->h_out_off = (unsigned long long *)malloc(nseg * 8);
-        if (!ctx->h_ntok || !ctx->h_btype || !ctx->h_out_bytes || !ctx->h_block_bits || !ctx->h_out_off) return DFL_E_MALLOC;
+        if (!ctx->h_ntok || !ctx->h_btype || !ctx->h_out_bytes || !ctx->h_cost || !ctx->h_block_bits || !ctx->h_out_off) return DFL_E_MALLOC;
         ctx->h_seg_cap = nseg;
     }
     return DFL_OK;
@@ -352,7 +366,15 @@ static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist
                         size_t nseg, uint8_t *d_out, size_t out_cap, cudaStream_t st)
 {
     const dfl_params prm = ctx->prm;
-    if (prm.chain_limit)
+    /* the default geometry (the window of a segment is the segment before it): runs of consecutive segments per
+     * CTA, the window's index inherited (k_match_run); anything else: one CTA per segment (k_match) */
+    if (!ctx->match_mode && prm.seg_bytes == DFL_MAX_SEG && prm.window == DFL_MAX_WINDOW && prm.use_dict && !prm.chain_limit) {
+        int run_segs = ns / (4 * ctx->num_sms);
+        run_segs = run_segs < 1 ? 1 : run_segs > RUN_SEGS ? RUN_SEGS : run_segs;
+        const int nruns = (ns + run_segs - 1) / run_segs;
+        LAUNCH(K_MATCH, k_match_run, nruns < ctx->num_sms ? nruns : ctx->num_sms, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n,
+               (long long)hist_len, (long long)s0, ns, run_segs, ctx->tokcand, ctx->scratch, ctx->state);
+    } else if (prm.chain_limit)
         LAUNCH(K_MATCH, k_match<true>, ns, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n, (long long)hist_len,
                (long long)s0, prm, ctx->tokcand, ctx->scratch, ctx->state);
     else
@@ -422,6 +444,7 @@ extern "C" int dfl_b200_deflate_enqueue(dfl_ctx *ctx, const uint8_t *d_in, size_
             CK(cudaMemcpyAsync(ctx->h_ntok + s0, ctx->A.ntok, ns * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_btype + s0, ctx->A.btype, ns * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_out_bytes + s0, ctx->A.out_bytes, ns * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_cost + 2 * s0, ctx->A.cost, ns * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_block_bits + s0, ctx->A.block_bits, ns * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_out_off + s0, ctx->A.out_off, ns * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -615,6 +638,9 @@ extern "C" int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info)
     info->block_bits = (int64_t)ctx->h_block_bits[seg];
     info->out_bytes = (int64_t)ctx->h_out_bytes[seg];
     info->out_offset = (int64_t)ctx->h_out_off[seg];
+    info->tree_bits = (int64_t)ctx->h_cost[2 * seg];
+    info->d_bits = (int64_t)ctx->h_cost[2 * seg + 1];
+    info->ll_bits = info->block_bits - 3 - info->tree_bits - info->d_bits;
     return DFL_OK;
 }
 

@@ -7,6 +7,7 @@
  */
 #define _GNU_SOURCE
 #include <errno.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -108,7 +109,10 @@ static int read_all(int fd, unsigned char **pbuf, size_t *pn)
     return 0;
 }
 
-/* One struct compress_stats per token (src/deflate_compress.c:291-309). */
+/* One struct compress_stats per token (src/deflate_compress.c:291-309).  ll / d are the token; bytes counts the
+ * input consumed so far (+ 1, :235); the three cost fields are those of the block the token belongs to, so that
+ * the reference's rate = (tree_bits + ll_bits + d_bits) / bytes (src/include/deflate_ext.h:29-30) read at the last
+ * record of a block is that block's real cost (less its 3 header bits). */
 static int write_stats(deflate_compr_t *com)
 {
     long nseg = dfl_b200_num_segments(com->ctx), s;
@@ -122,12 +126,10 @@ static int write_stats(deflate_compr_t *com)
         if (nt < 0 || dfl_b200_seg_info(com->ctx, s, &info)) { rc = -E_INVAL; break; }
         for (k = 0; k < nt; k++) {
             uint32_t t = tok[k];
-            int hdr = info.btype == 2 ? (int)(info.block_bits) : 0;
-            (void)hdr;
             recs[k].bytes = bytes;
-            recs[k].tree_bits = 0;
-            recs[k].ll_bits = (int)info.block_bits;
-            recs[k].d_bits = 0;
+            recs[k].tree_bits = (int)info.tree_bits;
+            recs[k].ll_bits = (int)info.ll_bits;
+            recs[k].d_bits = (int)info.d_bits;
             if ((t >> 16) == 0) { recs[k].ll = (int)(t & 0xFF); recs[k].d = 0; bytes += 1; }
             else { recs[k].ll = (int)(t & 0xFFFF); recs[k].d = (int)(t >> 16); bytes += (int)(t & 0xFFFF); }
         }
@@ -148,6 +150,8 @@ static int deflate_compr_run(deflate_compr_t *com)
     if (com->err) return com->err;
     rc = read_all(com->fd_in, &in, &n);
     if (rc) return rc;
+    /* compress_stats.bytes is an int (src/include/deflate_ext.h:20): the record stream cannot describe more */
+    if (com->fd_stats >= 0 && n >= (size_t)INT_MAX) { free(in); return -E_RANGE; }
     dfl_b200_default_params(&prm);
     prm.window = com->sliding_window;
     cap = dfl_b200_bound(&prm, n) + 16;

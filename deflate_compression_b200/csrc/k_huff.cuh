@@ -212,25 +212,35 @@ k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
     __syncwarp();
     huff_lengths_warp(S.cl_freq, NCL, 7, S.cl_len, S.sc, lane);
 
-    /* exact costs */
+    /* exact costs; the distance part (symbols + extra bits, RFC 1951 3.2.5: dist symbol s >= 4 carries s/2 - 1 extra
+     * bits) is kept apart for the cost split of struct compress_stats (src/include/deflate_ext.h:19-31) */
     unsigned long long dyn = 0, fix = 0;
+    uint32_t d_dyn = 0, d_fix = 0;
     for (int s = lane; s < NLL; s += 32) {
         dyn += (unsigned long long)S.ll_freq[s] * S.ll_len[s];
         fix += (unsigned long long)S.ll_freq[s] * fixed_ll_len(s);
     }
     if (lane < ND) {
+        const uint32_t dx = lane >= 4 ? (uint32_t)(lane / 2 - 1) : 0u;
+        d_dyn = S.d_freq[lane] * (S.d_len[lane] + dx);
+        d_fix = S.d_freq[lane] * (5 + dx);
         dyn += (unsigned long long)S.d_freq[lane] * S.d_len[lane];
         fix += (unsigned long long)S.d_freq[lane] * 5;
     }
+    d_dyn = __reduce_add_sync(FULL, d_dyn);
+    d_fix = __reduce_add_sync(FULL, d_fix);
+    unsigned long long tree = 0; /* code-length code part of the dynamic header */
     if (lane < NCL) {
-        dyn += (unsigned long long)S.cl_freq[lane] * S.cl_len[lane];
-        if (lane == 16) dyn += 2ull * S.cl_freq[16];
-        if (lane == 17) dyn += 3ull * S.cl_freq[17];
-        if (lane == 18) dyn += 7ull * S.cl_freq[18];
+        tree = (unsigned long long)S.cl_freq[lane] * S.cl_len[lane];
+        if (lane == 16) tree += 2ull * S.cl_freq[16];
+        if (lane == 17) tree += 3ull * S.cl_freq[17];
+        if (lane == 18) tree += 7ull * S.cl_freq[18];
+        dyn += tree;
     }
     for (int o = 16; o; o >>= 1) {
         dyn += __shfl_xor_sync(FULL, dyn, o);
         fix += __shfl_xor_sync(FULL, fix, o);
+        tree += __shfl_xor_sync(FULL, tree, o);
     }
     int btype = 0;
     unsigned long long block_bits = 0;
@@ -273,6 +283,8 @@ k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
             bw.put(1, 2);
         }
         A.hdr_bits[sl] = bw.nbits;
+        A.cost[2 * (size_t)sl] = btype == 2 ? (uint32_t)(tree + 5 + 5 + 4 + 3 * hclen) : 0u;
+        A.cost[2 * (size_t)sl + 1] = btype == 2 ? d_dyn : btype == 1 ? d_fix : 0u;
         A.btype[sl] = btype;
         A.block_bits[sl] = block_bits;
         A.out_bytes[sl] = btype == 0 ? (uint32_t)(seglen + 5 * nstored + 5)

@@ -28,6 +28,7 @@
 #define SORT_WARPS 32    /* every warp sorts one stripe */
 #define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
 #define SCRATCH_SLOTS 256
+#define SCRATCH_STRIDE NPOS_MAX /* u16 units per slot: k_match parks 64 Ki positions; k_match_run 32 Ki + the window block's bucket offsets */
 
 struct MatchSmem {
     uint32_t data[(NPOS_MAX + 64) / 4]; /* [window | segment] bytes, 16 B of slack either side */
@@ -88,8 +89,8 @@ __device__ __forceinline__ uint32_t cnt_shift(uint32_t d) { return (d & 1) * 16;
  *          cycles of a unit shared by the whole SM).
  */
 template <int PASS, bool FAST>
-__device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k_lo, int k_hi, int SS, const uint16_t *gbuf,
-                                              int lane, int warp, int sb)
+__device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int pos0, int lofs, int k_lo, int k_hi, int SS,
+                                              const uint16_t *gbuf, int lane, int warp, int sb)
 {
     const uint32_t ss_inv = SS ? 0xFFFFFFFFu / (uint32_t)SS + 1u : 0u; /* x / SS == umulhi(x, ss_inv) for x * SS < 2^32 */
     const uint32_t ngrp = HASH_SIZE >> sb;
@@ -97,7 +98,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>(S.off) + (PASS == 1 ? 0 : CNT_WORDS);
     volatile uint16_t *cnt16 = reinterpret_cast<volatile uint16_t *>(cnt32);
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
-    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list) + 2 * lofs;
     uint32_t cbase = (uint32_t)__cvta_generic_to_shared(S.off) + (PASS == 1 ? 0 : CNT_WORDS * 4);
     asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(cbase)); /* keep the window addresses in registers */
     const uint32_t c2base = cbase + CNT_WORDS * 4; /* only used by pass 1 */
@@ -113,9 +114,9 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
 #pragma unroll
         for (int j = 0; j < 4; j++) { /* bytes + bucket digit of the round's 4 steps: independent work first */
             const int k = k0 + j * 32 + lane;
-            e[j] = PASS == 1 ? (uint32_t)k : eq[j];
+            e[j] = PASS == 1 ? (uint32_t)(pos0 + k) : eq[j];
             if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
-            const uint32_t b = hash4(ld4s(dbase + (k < k_hi ? e[j] : 0)), ngrp, sb);
+            const uint32_t b = hash4(ld4s(dbase + (k < k_hi ? e[j] : (uint32_t)pos0)), ngrp, sb);
             d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
             d2[j] = b / SORT_BINS;
         }
@@ -162,8 +163,8 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int k
  * atomics), the scatter of a stripe is done in order by its warp.
  */
 template <int PASS, bool FAST>
-__device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, const uint16_t *gbuf, int tid, int lane, int warp,
-                                          DevState *state, int sb)
+__device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int pos0, int lofs, int NI, const uint16_t *gbuf, int tid,
+                                          int lane, int warp, DevState *state, int sb)
 {
     const uint32_t ngrp = HASH_SIZE >> sb;
     long long c0 = clock64(), c1;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
         /* count the low digits: every thread takes 8 consecutive positions; their 8 trigrams come
          * out of three unaligned word reads */
         for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
-            const uint32_t w0 = ld4s(dbase + k8), w1 = ld4s(dbase + k8 + 4), w2 = ld4s(dbase + k8 + 8);
+            const uint32_t w0 = ld4s(dbase + pos0 + k8), w1 = ld4s(dbase + pos0 + k8 + 4), w2 = ld4s(dbase + pos0 + k8 + 8);
             const uint32_t sw = __umulhi((uint32_t)k8, ss_inv); /* 8 | SS: the 8 positions share a stripe */
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -211,33 +212,33 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int NI, c
     STAMP2(9);
     {
         const int k_lo = warp * SS, k_hi = (k_lo + SS < NI) ? k_lo + SS : NI;
-        scatter_sweep<PASS, FAST>(S, soff, k_lo, k_hi, SS, gbuf, lane, warp, sb);
+        scatter_sweep<PASS, FAST>(S, soff, pos0, lofs, k_lo, k_hi, SS, gbuf, lane, warp, sb);
     }
     __syncthreads();
     STAMP2(10);
 #undef STAMP2
 }
 
-/* Sort the NI indexed positions by (bucket, position) into S.list and fill the
- * bucket offsets.  Returns (to every thread) whether the order verified. */
+/* Sort the NI positions [pos0, pos0 + NI) by (bucket, position) into S.list[lofs, lofs + NI) and fill the
+ * bucket offsets (relative to lofs).  Returns (to every thread) whether the order verified. */
 template <bool FAST>
-__device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI, uint16_t *gbuf, int tid, int lane, int warp,
-                                            DevState *state, int sb)
+__device__ __noinline__ bool build_index(MatchSmem &S, uint32_t soff, int pos0, int lofs, int NI, uint16_t *gbuf, int tid, int lane,
+                                            int warp, DevState *state, int sb)
 {
     const uint32_t ngrp = HASH_SIZE >> sb;
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
-    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list) + 2 * lofs;
     uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
     asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
     long long c0 = clock64(), c1;
 #define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
-    sort_pass<1, FAST>(S, soff, NI, gbuf, tid, lane, warp, state, sb);
+    sort_pass<1, FAST>(S, soff, pos0, lofs, NI, gbuf, tid, lane, warp, state, sb);
     STAMP(4);
     /* park the pass-1 order in global scratch: linear, 16 B per thread */
     for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8)
-        __stcg(reinterpret_cast<uint4 *>(gbuf + k8), *reinterpret_cast<const uint4 *>(&S.list[k8]));
+        __stcg(reinterpret_cast<uint4 *>(gbuf + k8), *reinterpret_cast<const uint4 *>(&S.list[lofs + k8]));
     STAMP(5);
-    sort_pass<2, FAST>(S, soff, NI, gbuf, tid, lane, warp, state, sb);
+    sort_pass<2, FAST>(S, soff, pos0, lofs, NI, gbuf, tid, lane, warp, state, sb);
     STAMP(6);
     /* bucket offsets from the sorted order (off[b] = first slot whose bucket is >= b), and
      * the check that every bucket is in ascending position order.  Slot kk is compared with
@@ -245,6 +246,7 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
     bool bad = false;
     if (NI == 0) {
         for (int i = tid; i < HASH_SIZE + 2; i += MATCH_THREADS) S.off[i] = 0;
+        __syncthreads();
         return true;
     }
     /* every offset starts as "unset"; the first slot of each non-empty bucket writes its own; the
@@ -314,6 +316,8 @@ __device__ __forceinline__ bool build_index(MatchSmem &S, uint32_t soff, int NI,
 #undef STAMP
     return ok;
 }
+
+#include "k_search.cuh"
 
 /*
  * One CTA per segment: process_loop's match search AND its greedy token
@@ -444,331 +448,19 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     {
         unsigned int smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        uint16_t *gbuf = scratch + (size_t)(smid % SCRATCH_SLOTS) * NPOS_MAX; /* one CTA per SM: private slot */
-        if (!build_index<true>(S, soff, NI, gbuf, tid, lane, warp, state, sb)) {
+        uint16_t *gbuf = scratch + (size_t)(smid % SCRATCH_SLOTS) * SCRATCH_STRIDE; /* one CTA per SM: private slot */
+        if (!build_index<true>(S, soff, 0, 0, NI, gbuf, tid, lane, warp, state, sb)) {
             /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
             if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-            build_index<false>(S, soff, NI, gbuf, tid, lane, warp, state, sb);
+            build_index<false>(S, soff, 0, 0, NI, gbuf, tid, lane, warp, state, sb);
         }
     }
     const long long t2 = clock64();
 
-    /* ---- speculative chunk parsers ----
-     * Run by the first SEARCH_WARPS warps only: chains die as they merge, so with one chunk per lane
-     * half the lanes of a warp sit idle behind its slowest chain; fewer lanes that each take several
-     * chunks from the shared counter keep the warps' lanes occupied (the SM is issue bound: what counts
-     * is useful lanes per instruction, not resident warps). */
-    if (warp < SEARCH_WARPS) {
-        enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6, ST_LONG = 7 };
-        const int W = prm.window, K = HAS_K ? prm.chain_limit : 0;
-        const uint32_t ngrp = HASH_SIZE >> sb;
-        /* first filter of a walk: 4 bytes when the buckets are split (the walk only looks for matches
-         * of >= 4, the trigram sweep does the rest), the trigram otherwise */
-        const uint32_t fmask0 = sb ? 0xFFFFFFFFu : 0xFFFFFFu;
-        /* shared-window addresses held in registers (the empty asm keeps ptxas from re-deriving them
-         * from special registers inside the loops) */
-        uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff; /* data byte 0 */
-        uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
-        uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
-        asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
-        const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
-        uint32_t *out = tokcand + (size_t)blockIdx.x * prm.seg_bytes;
-        int st = ST_IDLE;
-        int i = 0, p = 0, q = 0, k = 0, k_lo = 0, k_hi = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
-        uint32_t pw0 = 0, pw1 = 0, fword = 0, fmask = 0;
-        int foff = 0;
-
-        /* take position i_ as a parse head (caller has claimed it) */
-#define INIT_HEAD(i_)                                                                   \
-        do {                                                                            \
-            i = (i_);                                                                   \
-            p = hist + i;                                                               \
-            maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;           \
-            best_len = 2; best_dist = 0; hops = 0;                                      \
-            if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                               \
-            else {                                                                      \
-                pw0 = ld4s(dbase + p);                                                  \
-                if (sb && maxlen == DFL_MIN_MATCH) { st = ST_DONE; } /* split buckets: only the trigram sweep applies */ \
-                else {                                                                  \
-                    st = ST_SEEK;                                                       \
-                    pw1 = ld4s(dbase + p + 4);                                          \
-                    foff = 0; fmask = fmask0; fword = pw0 & fmask0;                     \
-                    const uint32_t b_ = hash4(pw0, ngrp, sb);                           \
-                    k_lo = (int)lds_u16(obase + 2 * b_);                                \
-                    k = k_lo;                                                           \
-                    k_hi = (int)lds_u16(obase + 2 * b_ + 2);                            \
-                }                                                                       \
-            }                                                                           \
-        } while (0)
-
-#ifdef DFL_SEARCH_STATS
-        unsigned long long sx_iter = 0, sx_walk = 0, sx_fin = 0, sx_done = 0, sx_cand = 0, sx_heads = 0, sx_hops = 0, sx_seek = 0;
-#endif
-        for (;;) {
-#ifdef DFL_SEARCH_STATS
-            {
-                const uint32_t c1 = __reduce_add_sync(FULL, (st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) | (st == ST_DONE ? 0x10000u : 0u));
-                sx_iter++; sx_walk += c1 & 0xFF; sx_fin += (c1 >> 8) & 0xFF; sx_done += c1 >> 16;
-            }
-#endif
-            /* phase A: walk the bucket backwards until a candidate passes the 4-byte filter.  Without a chain
-             * limit two entries are fetched per step: their list and data loads overlap (the loop is bound by
-             * the dependent shared-memory latency of a hop, not by issue slots). */
-            if (st == ST_WALK) {
-                if (HAS_K) {
-#pragma unroll 1
-                    for (int t = 0; t < HOP_BATCH; t++) {
-                        if (k <= k_lo || hops >= K) { st = ST_DONE; break; }
-                        q = (int)lds_u16(lbase + 2 * (--k));
-                        if (p - q > W) { st = ST_DONE; break; }
-                        hops++;
-                        /* filter: the 4 bytes ending at offset best_len (fmask0 while nothing is found
-                         * yet) must match for q to beat the best so far */
-                        if ((ld4s(dbase + q + foff) & fmask) == fword) { st = ST_CAND; break; }
-                    }
-                } else {
-#pragma unroll 1
-                    for (int t = 0; t < HOP_BATCH; t += 2) {
-                        if (k <= k_lo) { st = ST_DONE; break; }
-                        const int q1 = (int)lds_u16(lbase + 2 * (k - 1));
-                        const int q2 = k - 1 > k_lo ? (int)lds_u16(lbase + 2 * (k - 2)) : p - W - 1; /* no second entry: reads as "outside the window" */
-                        const uint32_t w1 = ld4s(dbase + q1 + foff), w2 = ld4s(dbase + (q2 < 0 ? 0 : q2) + foff);
-#ifdef DFL_SEARCH_STATS
-                        sx_hops += 2;
-#endif
-                        const bool o1 = p - q1 > W, h1 = (w1 & fmask) == fword, o2 = p - q2 > W, h2 = (w2 & fmask) == fword;
-                        if (o1 | h1 | o2 | h2) { /* one exit; which of the four it was is sorted out off the hot path */
-                            if (o1) { st = ST_DONE; k -= 1; }
-                            else if (h1) { st = ST_CAND; q = q1; k -= 1; }
-                            else if (o2) { st = ST_DONE; k -= 2; }
-                            else { st = ST_CAND; q = q2; k -= 2; }
-                            break;
-                        }
-                        k -= 2;
-                    }
-                }
-            }
-#ifdef DFL_SEARCH_STATS
-            sx_cand += __reduce_add_sync(FULL, st == ST_CAND ? 1u : 0u);
-#endif
-            /* a long remainder of the bucket is walked by the whole warp together (phase C) */
-            if (st == ST_WALK) {
-                int rem = k - k_lo;
-                if (HAS_K && K - hops < rem) rem = K - hops;
-                if (rem > COOP_MIN) st = ST_HEAVY;
-            }
-            /* phase B: full compare (check_dup_str) for the lanes holding a candidate.  A lane compares up
-             * to LONG_CMP_FROM bytes on its own; a match still running then (logs, runs, images: up to 258
-             * bytes = 64 dependent steps for one lane) is finished by the whole warp, 128 bytes per step. */
-#define APPLY_LEN(len_)                                                                               \
-            do {                                                                                      \
-                int l_ = (len_);                                                                      \
-                if (l_ > maxlen) l_ = maxlen;                                                         \
-                st = ST_WALK;                                                                         \
-                if (l_ > best_len) {                                                                  \
-                    best_len = l_;                                                                    \
-                    best_dist = p - q;                                                                \
-                    if (l_ == maxlen) st = ST_DONE;                                                   \
-                    else { foff = l_ - 3; fmask = 0xFFFFFFFFu; fword = ld4s(dbase + p + foff); }      \
-                }                                                                                     \
-            } while (0)
-            int long_from = 0;
-            if (st == ST_CAND) {
-                int len;
-                const uint32_t x0 = ld4s(dbase + q) ^ pw0, x1 = ld4s(dbase + q + 4) ^ pw1; /* both loads in flight together */
-                if (x0) {
-                    len = (__ffs(x0) - 1) >> 3;
-                } else if (x1) {
-                    len = 4 + ((__ffs(x1) - 1) >> 3);
-                } else {
-                    len = 8;
-                    while (len < maxlen && len < LONG_CMP_FROM) {
-                        const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
-                        if (x) { len += (__ffs(x) - 1) >> 3; long_from = -1; break; }
-                        len += 4;
-                    }
-                    if (long_from == 0 && len < maxlen) long_from = len; /* still equal at LONG_CMP_FROM bytes */
-                    else long_from = 0;
-                }
-                if (long_from) st = ST_LONG;
-                else APPLY_LEN(len);
-            }
-            /* phase C: finished heads emit their token and move on; idle lanes take new
-             * chunks.  One warp reduction per round steers it (votes and shuffles share a
-             * slow unit on this chip). */
-            const uint32_t census = __reduce_add_sync(FULL, (st == ST_WALK ? 1u : 0u) | (st == ST_FIN ? 0x100u : 0u) |
-                                                                (st == ST_HEAVY ? 0x10000u : 0u) | (st == ST_LONG ? 0x1000000u : 0u));
-            const int n_busy = census & 0xFF, n_fin = (census >> 8) & 0xFF, n_heavy = (census >> 16) & 0xFF, n_long = census >> 24;
-            if (n_fin == 32) break;
-            if (n_long)
-            {
-                uint32_t lng = __ballot_sync(FULL, st == ST_LONG);
-                while (lng) {
-                    const int L = __ffs(lng) - 1;
-                    lng &= lng - 1;
-                    const int hp = __shfl_sync(FULL, p, L), hq = __shfl_sync(FULL, q, L), hmax = __shfl_sync(FULL, maxlen, L);
-                    const int l0 = __shfl_sync(FULL, long_from, L);
-                    int flen = hmax;
-                    for (int base = l0; base < hmax; base += 128) {
-                        const int off_ = base + 4 * lane;
-                        const uint32_t x = off_ < hmax ? ld4s(dbase + hp + off_) ^ ld4s(dbase + hq + off_) : 1u; /* the end reads as a mismatch */
-                        const uint32_t m = __ballot_sync(FULL, x != 0);
-                        if (m) {
-                            const int f = __ffs(m) - 1;
-                            const uint32_t xf = __shfl_sync(FULL, x, f);
-                            const int fo = base + 4 * f;
-                            flen = fo < hmax ? fo + ((__ffs(xf) - 1) >> 3) : hmax;
-                            break;
-                        }
-                    }
-                    if (lane == L) APPLY_LEN(flen);
-                }
-            }
-#undef APPLY_LEN
-            if (n_heavy) {
-                /* cooperative walk: the 32 lanes take 32 consecutive bucket entries per pass,
-                 * nearest first; one warp reduction per pass picks the longest (then nearest)
-                 * improvement and tightens the filter for the next pass.  Same result as the
-                 * sequential walk: strict improvement only, nearer passes first. */
-                uint32_t heavy = __ballot_sync(FULL, st == ST_HEAVY);
-                while (heavy) {
-                    const int L = __ffs(heavy) - 1;
-                    heavy &= heavy - 1;
-                    const int hp = __shfl_sync(FULL, p, L), hk = __shfl_sync(FULL, k, L);
-                    int hlo = __shfl_sync(FULL, k_lo, L);
-                    const int hmax = __shfl_sync(FULL, maxlen, L);
-                    const uint32_t hw0 = __shfl_sync(FULL, pw0, L), hw1 = __shfl_sync(FULL, pw1, L);
-                    const int hhops = HAS_K ? __shfl_sync(FULL, hops, L) : 0;
-                    if (HAS_K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
-                    int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
-                    int hfoff = hbest == 2 ? 0 : hbest - 3;
-                    uint32_t hfmask = hbest == 2 ? fmask0 : 0xFFFFFFFFu;
-                    uint32_t hfword = ld4s(dbase + hp + hfoff) & hfmask;
-                    for (int top = hk; top > hlo; top -= 32) {
-                        const int kk = top - 1 - lane;
-                        bool valid = kk >= hlo;
-                        const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
-                        valid = valid && (hp - cq <= W);
-                        uint32_t key = valid ? 0x80000000u : 0u;
-                        if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {
-                            int len;
-                            uint32_t x = ld4s(dbase + cq) ^ hw0;
-                            if (x) {
-                                len = (__ffs(x) - 1) >> 3;
-                            } else {
-                                x = ld4s(dbase + cq + 4) ^ hw1;
-                                if (x) {
-                                    len = 4 + ((__ffs(x) - 1) >> 3);
-                                } else {
-                                    len = 8;
-                                    while (len < hmax) {
-                                        x = ld4s(dbase + hp + len) ^ ld4s(dbase + cq + len);
-                                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                                        len += 4;
-                                    }
-                                }
-                            }
-                            if (len > hmax) len = hmax;
-                            if (len > hbest) key |= ((uint32_t)len << 16) | (uint32_t)(0xFFFF - (hp - cq));
-                        }
-                        const uint32_t kmax = __reduce_max_sync(FULL, key);
-                        if (!(kmax >> 31)) break; /* the whole pass is outside the window */
-                        if (kmax & 0x7FFFFFFFu) {
-                            hbest = (kmax >> 16) & 0x7FFF;
-                            hdist = 0xFFFF - (kmax & 0xFFFF);
-                            if (hbest == hmax) break;
-                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4s(dbase + hp + hfoff);
-                        }
-                    }
-                    if (lane == L) { best_len = hbest; best_dist = hdist; st = ST_DONE; }
-                }
-            }
-            if (32 - n_busy - n_fin >= REFILL_MIN_IDLE || n_busy == 0) {
-                /* Heads whose own bucket held no match of >= 4 bytes: the answer is the NEAREST earlier
-                 * occurrence of the trigram (all remaining matches have length exactly 3, :258 keeps the
-                 * first found), which lives somewhere in the 2^DFL_SUB_BITS buckets of the trigram's group.
-                 * The group is one contiguous range of the list: the warp sweeps it flat, one head at a
-                 * time, and keeps the largest matching position inside the window. */
-                uint32_t need = sb ? __ballot_sync(FULL, st == ST_DONE && best_len == 2 && maxlen >= DFL_MIN_MATCH) : 0u;
-                while (need) {
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int hp = __shfl_sync(FULL, p, L);
-                    const uint32_t hw = __shfl_sync(FULL, pw0, L) & 0xFFFFFFu;
-                    const uint32_t g_ = hash4(hw, ngrp, sb); /* fourth byte 0 -> first bucket of the group */
-                    const int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
-                    uint32_t loc = 0;
-                    for (int kk = ghi - 1 - lane; kk >= glo; kk -= 64) { /* two steps' loads in flight together */
-                        const int kb = kk - 32;
-                        const int cq = (int)lds_u16(lbase + 2 * kk), cq2 = kb >= glo ? (int)lds_u16(lbase + 2 * kb) : hp;
-                        const int d = hp - cq, d2 = hp - cq2;
-                        const bool in1 = (unsigned)(d - 1) < (unsigned)W, in2 = (unsigned)(d2 - 1) < (unsigned)W;
-                        const uint32_t t1 = in1 ? ld4s(dbase + cq) & 0xFFFFFFu : ~hw, t2 = in2 ? ld4s(dbase + cq2) & 0xFFFFFFu : ~hw;
-                        if (t1 == hw && (uint32_t)cq + 1 > loc) loc = (uint32_t)cq + 1;
-                        if (t2 == hw && (uint32_t)cq2 + 1 > loc) loc = (uint32_t)cq2 + 1;
-                    }
-                    loc = __reduce_max_sync(FULL, loc);
-                    if (lane == L && loc) { best_len = DFL_MIN_MATCH; best_dist = p - (int)(loc - 1); }
-                }
-                if (st == ST_DONE) {
-                    int adv = 1;
-                    uint32_t t = lds_u8(dbase + p);
-                    if (best_len >= DFL_MIN_MATCH) {
-                        t = ((uint32_t)best_dist << 16) | (uint32_t)best_len;
-                        adv = best_len;
-                    }
-                    out[i] = t;
-#ifdef DFL_SEARCH_STATS
-                    sx_heads++;
-#endif
-                    st = ST_IDLE;
-                    const int ni = i + adv;
-                    if (ni < seglen) {
-                        const uint32_t bit = 1u << (ni & 31);
-                        if (!(atomicOr(&S.claimed[ni >> 5], bit) & bit)) INIT_HEAD(ni);
-                    }
-                }
-                if (st == ST_IDLE) {
-                    const int c = atomicAdd(&S.next_chunk, 1);
-                    if (c >= nchunks) {
-                        st = ST_FIN;
-                    } else {
-                        const int ci = c * MATCH_CHUNK;
-                        const uint32_t bit = 1u << (ci & 31);
-                        /* a chain that has already claimed a head inside this chunk covers it (it runs until
-                         * it meets a claimed head); starting here too would only add speculative heads */
-                        const bool entered = SKIP_OVERRUN && MATCH_CHUNK == 32 && S.claimed[ci >> 5] != 0;
-                        if (!entered && !(atomicOr(&S.claimed[ci >> 5], bit) & bit)) INIT_HEAD(ci);
-                    }
-                }
-                /* the new heads find their own slot in their bucket together: lower bound of p in
-                 * list[k, k_hi); candidates are then k-1 ... k_lo */
-                if (st == ST_SEEK) {
-#ifdef DFL_SEARCH_STATS
-                    sx_seek++;
-#endif
-                    while (k < k_hi) {
-                        const int mid = (k + k_hi) >> 1;
-                        if ((int)lds_u16(lbase + 2 * mid) < p) k = mid + 1; else k_hi = mid;
-                    }
-                    st = ST_WALK;
-                }
-            }
-        }
-#ifdef DFL_SEARCH_STATS
-        sx_heads = __reduce_add_sync(FULL, (uint32_t)sx_heads);
-        sx_hops = __reduce_add_sync(FULL, (uint32_t)sx_hops);
-        sx_seek = __reduce_add_sync(FULL, (uint32_t)sx_seek);
-        if (lane == 0) {
-            atomicAdd(&state->t_phase[12], sx_iter); atomicAdd(&state->t_phase[13], sx_walk);
-            atomicAdd(&state->t_phase[14], sx_fin); atomicAdd(&state->t_phase[15], sx_done);
-            atomicAdd(&state->t_phase[16], sx_cand); atomicAdd(&state->t_phase[17], sx_heads);
-            atomicAdd(&state->t_phase[18], sx_hops); atomicAdd(&state->t_phase[19], sx_seek);
-            S.scan_w[warp] = (uint32_t)(clock64() - t2); /* when this warp ran out of work */
-        }
-#endif
-#undef INIT_HEAD
-    }
+    /* ---- speculative chunk parsers (k_search.cuh) ---- */
+    if (warp < SEARCH_WARPS)
+        search_segment<HAS_K, false>(S, soff, hist, seglen, prm.window, HAS_K ? prm.chain_limit : 0, sb,
+                                     tokcand + (size_t)blockIdx.x * prm.seg_bytes, nullptr, state, lane, warp, t2);
     __syncthreads();
 #ifdef DFL_SEARCH_STATS
     if (warp == 0 && warp < SEARCH_WARPS) {

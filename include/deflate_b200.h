@@ -76,6 +76,11 @@ typedef struct dfl_seg_info {
     int64_t block_bits;  /* chosen block incl. 3 header bits, excl. sync marker */
     int64_t out_bytes;   /* bytes of this segment in the stream incl. sync marker */
     int64_t out_offset;  /* byte offset of the segment in the deflate body */
+    /* the block's cost the way struct compress_stats splits it (src/include/deflate_ext.h:19-31);
+     * tree_bits + ll_bits + d_bits + 3 == block_bits */
+    int64_t tree_bits;   /* code description: HLIT/HDIST/HCLEN, code-length code, run-length coded lengths (0 unless dynamic) */
+    int64_t ll_bits;     /* lit/len symbols + length extra bits (stored: everything but the 3 header bits) */
+    int64_t d_bits;      /* distance symbols + distance extra bits */
 } dfl_seg_info;
 
 void dfl_b200_default_params(dfl_params *p);
@@ -162,6 +167,12 @@ int dfl_b200_png_encode_host(dfl_ctx *ctx, const uint8_t *pix, uint32_t width, u
 /* Which kernel resolves the greedy parse of a chunk: 0 = chosen by the chunk's segment count (default),
  * 1 = one warp per segment (k_parse_warp), 2 = one CTA per segment (k_parse).  Same tokens either way. */
 int dfl_b200_set_parse_mode(dfl_ctx *ctx, int mode);
+
+/* Which kernel builds the index and searches: 0 = k_match_run (runs of consecutive segments per CTA, the window's
+ * sorted index inherited from the segment before) wherever the geometry is the default one (segments and window
+ * of 32768 bytes, dictionary priming, no chain limit) and k_match (one CTA per segment) elsewhere; 1 = always
+ * k_match.  Same tokens either way. */
+int dfl_b200_set_match_mode(dfl_ctx *ctx, int mode);
 
 /* Number of kernels this context has launched (bench.py's gpu_launches). */
 long dfl_b200_kernel_launches(dfl_ctx *ctx);

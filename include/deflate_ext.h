@@ -55,13 +55,16 @@ int deflate_decompress(struct string_len *decompr_dat, struct string_len *compr_
 int deflate_compress(int fd_in, int fd_out, int fd_stats, swi sw, int ops);
 
 /* Per-token record on fd_stats, src/include/deflate_ext.h:19-31.  In this
- * implementation the three cost fields are block-level (the cost of the block the
- * token belongs to), not the reference's running per-token estimate. */
+ * implementation the three cost fields are block-level (the exact cost of the block
+ * the token belongs to, every token of a block carries the same three numbers), not
+ * the reference's running per-token estimate: tree_bits + ll_bits + d_bits + 3 header
+ * bits = the block's size in bits.  bytes is an int as in the reference, so
+ * deflate_compress() returns -E_RANGE for inputs of 2 GiB or more when fd_stats >= 0. */
 struct compress_stats {
     int bytes;     /* input bytes consumed before this token, + 1 */
-    int tree_bits; /* bits of the block's code description */
-    int ll_bits;   /* bits of the block's lit/len + distance symbols and extra bits */
-    int d_bits;    /* 0 (folded into ll_bits) */
+    int tree_bits; /* bits of the block's code description (dynamic blocks; else 0) */
+    int ll_bits;   /* bits of the block's lit/len symbols + length extra bits (stored block: its bytes + LEN/NLEN + padding) */
+    int d_bits;    /* bits of the block's distance symbols + distance extra bits */
     int ll;        /* literal byte, or match length */
     int d;         /* 0 for a literal, else match distance */
 };

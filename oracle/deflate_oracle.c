@@ -469,7 +469,7 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
     uint32_t ll_freq[ORC_NUM_LL + 2], d_freq[ORC_NUM_D + 2], cl_freq[ORC_NUM_CL];
     orc_dyn dy;
     uint8_t seq[ORC_NUM_LL + ORC_NUM_D + 4];
-    int64_t extra_bits = 0, fixed_bits, dyn_bits, stored_bits;
+    int64_t extra_bits = 0, d_extra_bits = 0, fixed_bits, dyn_bits, stored_bits;
     long k, nstored, start_pos = bw->pos;
     int s, eb, ev, btype, i;
 
@@ -485,6 +485,7 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
             extra_bits += eb;
             d_freq[orc_dist_sym((int)ORC_TOK_DIST(t), &eb, &ev)]++;
             extra_bits += eb;
+            d_extra_bits += eb;
         }
     }
     ll_freq[256]++; /* end of block, counted once: src/deflate_compress.c:233-234 */
@@ -594,6 +595,19 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
         st->dynamic_bits = dyn_bits;
         st->block_bits = btype == 0 ? stored_bits : btype == 1 ? fixed_bits : dyn_bits;
         st->out_bytes = bw->pos - start_pos;
+        /* cost split (what the reference's per-token record estimates, src/deflate_compress.c:291-309) */
+        st->tree_bits = 0;
+        st->d_bits = 0;
+        if (btype == 0) {
+            st->ll_bits = stored_bits - 3;
+        } else {
+            int64_t llb = extra_bits - d_extra_bits, db = d_extra_bits;
+            for (s = 0; s < ORC_NUM_LL; s++) llb += (int64_t)ll_freq[s] * (btype == 2 ? dy.ll_len[s] : orc_fixed_ll_len(s));
+            for (s = 0; s < ORC_NUM_D; s++) db += (int64_t)d_freq[s] * (btype == 2 ? dy.d_len[s] : 5);
+            st->ll_bits = llb;
+            st->d_bits = db;
+            st->tree_bits = st->block_bits - 3 - llb - db;
+        }
     }
 }
 

@@ -54,6 +54,11 @@ typedef struct orc_seg_stats {
     int64_t block_bits;  /* bits of the block(s) incl. 3-bit header, excl. sync marker */
     int64_t out_bytes;   /* bytes of the segment incl. sync marker */
     int64_t stored_bits, fixed_bits, dynamic_bits;
+    /* the chosen block's cost split the way struct compress_stats reports it (src/include/deflate_ext.h:19-31):
+     * tree_bits + ll_bits + d_bits + 3 == block_bits */
+    int64_t tree_bits; /* code description: HLIT/HDIST/HCLEN, code-length code, run-length coded lengths (0 unless dynamic) */
+    int64_t ll_bits;   /* lit/len symbols + length extra bits (stored: everything but the 3 header bits) */
+    int64_t d_bits;    /* distance symbols + distance extra bits */
 } orc_seg_stats;
 
 void orc_default_params(orc_params *p);

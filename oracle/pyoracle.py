@@ -40,6 +40,9 @@ class OrcSegStats(C.Structure):
         ("stored_bits", C.c_int64),
         ("fixed_bits", C.c_int64),
         ("dynamic_bits", C.c_int64),
+        ("tree_bits", C.c_int64),
+        ("ll_bits", C.c_int64),
+        ("d_bits", C.c_int64),
     ]
 
 

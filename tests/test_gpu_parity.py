@@ -168,6 +168,16 @@ def test_fd_api_roundtrip(D, O, tmp_path):
                 out.append(out[-int(d)])
     assert bytes(out) == data.tobytes()
     assert toks.size == recs.shape[0]
+    # cost fields: every token carries its block's split (tree / lit-len / distance bits), == the oracle's
+    body, stats = O.deflate_body(data, 0, data.size, O.params())
+    k = 0
+    for s_, stt in enumerate(stats):
+        blk = recs[k:k + stt.ntokens]
+        assert blk.shape[0] == stt.ntokens
+        assert (blk[:, 1] == stt.tree_bits).all() and (blk[:, 2] == stt.ll_bits).all() and (blk[:, 3] == stt.d_bits).all(), s_
+        assert int(blk[0, 1]) + int(blk[0, 2]) + int(blk[0, 3]) + 3 == stt.block_bits
+        k += stt.ntokens
+    assert k == recs.shape[0]
 
 
 def test_fd_api_pipe_and_errors(D):
@@ -424,6 +434,71 @@ def test_parse_kernels_agree(D, O, mode, kind, seed, n):
         lo, hi = s * 32768, min(n, (s + 1) * 32768)
         assert np.array_equal(comp.tokens(s), O.lz77_segment(data, 0, lo, hi, op)), f"mode {mode} segment {s}"
     assert z == O.zlib_compress(data, op)
+    comp.close()
+
+
+@pytest.mark.parametrize("kind,seed,n", [("markov", 15, 1200001), ("random", 16, 300000), ("log", 17, 700000), ("png", 18, 500000),
+                                         ("zeros", 0, 200000), ("period7", 0, 150000), ("markov", 19, 32768 * 3 + 1),
+                                         ("markov", 19, 32768 * 2 + 2), ("markov", 19, 32768 * 2), ("markov", 20, 40)])
+def test_match_kernels_agree(D, O, kind, seed, n):
+    """k_match_run (runs of consecutive segments per CTA, the window's sorted index inherited) and k_match (one
+    CTA per segment, window and segment sorted together) find the same tokens: == the oracle's with either one,
+    and the streams are identical."""
+    data = make_input(kind, seed, 0, n)
+    op = O.params()
+    streams = []
+    for mode in (0, 1):
+        comp = D.Compressor()
+        comp.set_match_mode(mode)
+        comp.keep_tokens(True)
+        streams.append(comp.compress(data))
+        for s in range(comp.num_segments()):
+            lo, hi = s * 32768, min(n, (s + 1) * 32768)
+            assert np.array_equal(comp.tokens(s), O.lz77_segment(data, 0, lo, hi, op)), f"match mode {mode} segment {s}"
+        assert comp.sort_fallbacks() == 0
+        comp.close()
+    assert streams[0] == streams[1] == O.zlib_compress(data, op)
+
+
+def test_match_run_shard_with_partial_history(D, O):
+    """k_match_run on a shard whose history is shorter than a window (and not a multiple of 16): the first
+    segment's window block is partial, later ones inherit."""
+    import torch
+
+    whole = make_input("markov", 23, 0, 500000)
+    for hist in (0, 1, 777, 32767, 32768):
+        lo = 40000
+        dev = torch.device("cuda:0")
+        d_all = torch.from_numpy(whole).to(dev)
+        comp = D.Compressor()
+        comp.keep_tokens(True)
+        n = whole.size - lo
+        cap = comp.bound(n)
+        d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        comp.deflate_device(d_all.data_ptr() + lo, n, hist, True, d_out.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
+        op = O.params()
+        for s in range(comp.num_segments()):
+            a, b = lo + s * 32768, min(whole.size, lo + (s + 1) * 32768)
+            want = O.lz77_segment(whole, lo - hist, a, b, op)
+            assert np.array_equal(comp.tokens(s), want), f"hist {hist} segment {s}"
+        comp.close()
+
+
+@pytest.mark.parametrize("prm", [dict(), dict(block_mode=1), dict(block_mode=2), dict(block_mode=3), dict(seg_bytes=5000)])
+def test_seg_info_cost_split(D, O, prm):
+    """dfl_seg_info's tree / lit-len / distance bits (k_huff) == the oracle's, and add up to the block."""
+    data = np.concatenate([make_input("markov", 44, 0, 100000), make_input("random", 45, 0, 40000),
+                           make_input("log", 46, 0, 70000), make_input("zeros", 0, 0, 40000)])
+    comp = D.Compressor(**prm)
+    comp.keep_tokens(True)
+    comp.compress(data)
+    body, stats = O.deflate_body(data, 0, data.size, O.params(**prm))
+    assert comp.num_segments() == len(stats)
+    for s_, stt in enumerate(stats):
+        info = comp.seg_info(s_)
+        assert (info.btype, info.block_bits) == (stt.btype, stt.block_bits), s_
+        assert (info.tree_bits, info.ll_bits, info.d_bits) == (stt.tree_bits, stt.ll_bits, stt.d_bits), s_
+        assert info.tree_bits + info.ll_bits + info.d_bits + 3 == info.block_bits
     comp.close()
 
 

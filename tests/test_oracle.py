@@ -65,6 +65,35 @@ def test_reference_cost_fields_against_oracle(O):
         assert abs(stats[0].dynamic_bits - ref_est) <= 0.01 * ref_est + 64, (name, stats[0].dynamic_bits, ref_est)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_cost_split_adds_up_and_matches_reference_fields(O, mode):
+    """tree_bits + ll_bits + d_bits + 3 == block_bits for every block type (struct compress_stats' split,
+    src/include/deflate_ext.h:19-31); for dynamic blocks ll_bits / d_bits less their extra bits are the Huffman
+    cost of the histogram, which the reference's last record estimates (its AHT is the unlimited optimum + 1 NYT
+    leaf), and tree_bits is what h_tree_d_lens sums (src/h_tree.c:75-148): both within 1 %."""
+    for case in golden_cases():
+        name, kind, seed, off, n, ref_toks, last, sha = case
+        data = make_input(kind, seed, off, n)
+        body, stats = O.deflate_body(data, 0, n, O.params(use_dict=0, block_mode=mode))
+        st = stats[0]
+        assert st.tree_bits + st.ll_bits + st.d_bits + 3 == st.block_bits, name
+        assert st.tree_bits >= 0 and st.ll_bits >= 0 and st.d_bits >= 0
+        if st.btype != 2:
+            assert st.tree_bits == 0
+        if st.btype == 0:
+            assert st.d_bits == 0 and st.ll_bits == 8 * (n + 5 * max(1, (n + 65534) // 65535)) - 3
+        if mode == 3 and n >= 3000:
+            lx = dx = 0
+            for t in ref_toks:
+                d, l = int(t) >> 16, int(t) & 0xFFFF
+                if d:
+                    lt, dt = l - 3, d - 1
+                    lx += 0 if (l == 258 or lt < 8) else (lt.bit_length() - 1) - 2
+                    dx += 0 if dt < 4 else (dt.bit_length() - 1) - 1
+            assert abs((st.ll_bits - lx) - int(last[2])) <= 0.01 * int(last[2]) + 32, (name, st.ll_bits - lx, int(last[2]))
+            assert abs((st.d_bits - dx) - int(last[3])) <= 0.01 * int(last[3]) + 32, (name, st.d_bits - dx, int(last[3]))
+
+
 @pytest.mark.parametrize("kind,seed", [("markov", 1), ("random", 4), ("log", 3), ("png", 6), ("zeros", 0),
                                         ("period7", 0)])
 @pytest.mark.parametrize("prm", [dict(), dict(seg_bytes=4096), dict(use_dict=0), dict(window=1024),
