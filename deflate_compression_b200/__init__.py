@@ -8,6 +8,7 @@ from .api import (  # noqa: F401
     DflParams,
     DflError,
     build,
+    compress_multi,
     deflate_compress,
     deflate_decompress,
     lib,

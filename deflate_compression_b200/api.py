@@ -106,6 +106,11 @@ def lib() -> C.CDLL:
         L.dfl_b200_tokens.restype = C.c_long
         L.dfl_b200_tokens.argtypes = [vp, C.c_long, vp, C.c_long]
         L.dfl_b200_set_match_mode.argtypes = [vp, C.c_int]
+        L.dfl_b200_compress_fd.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        L.dfl_b200_set_fd_piece.argtypes = [vp, C.c_size_t]
+        L.dfl_b200_compress_host_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.dfl_b200_adler32_combine.restype = C.c_uint32
+        L.dfl_b200_adler32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
         L.dfl_b200_kernel_launches.restype = C.c_long
         L.dfl_b200_kernel_launches.argtypes = [vp]
         L.dfl_b200_enable_timing.argtypes = [vp, C.c_int]
@@ -276,6 +281,15 @@ class Compressor:
         if rc:
             raise DflError(rc, "dfl_b200_set_parse_mode")
 
+    def compress_fd(self, fd_in: int, fd_out: int, piece_bytes: int = 0):
+        """fd -> fd (the body of deflate_compress): returns (bytes read, bytes written)."""
+        lib().dfl_b200_set_fd_piece(self._ctx, int(piece_bytes))
+        nin, nout = C.c_ulonglong(0), C.c_ulonglong(0)
+        rc = lib().dfl_b200_compress_fd(self._ctx, int(fd_in), int(fd_out), C.byref(nin), C.byref(nout))
+        if rc:
+            raise DflError(rc, "dfl_b200_compress_fd")
+        return int(nin.value), int(nout.value)
+
     def set_match_mode(self, mode: int) -> None:
         """0 = k_match_run where the geometry is the default one, 1 = always k_match (same tokens)."""
         rc = lib().dfl_b200_set_match_mode(self._ctx, int(mode))
@@ -322,6 +336,16 @@ class Compressor:
 
     def kernel_launches(self) -> int:
         return int(lib().dfl_b200_kernel_launches(self._ctx))
+
+
+def compress_multi(comps, in_ptr: int, n: int, out_ptr: int, cap: int) -> int:
+    """dfl_b200_compress_host_multi: comps = one Compressor per GPU (same parameters); host pointers; -> stream length."""
+    arr = (C.c_void_p * len(comps))(*[c._ctx.value for c in comps])
+    out_len = C.c_size_t(0)
+    rc = lib().dfl_b200_compress_host_multi(arr, len(comps), in_ptr, n, out_ptr, cap, C.byref(out_len))
+    if rc:
+        raise DflError(rc, "dfl_b200_compress_host_multi")
+    return int(out_len.value)
 
 
 def deflate_compress(fd_in: int, fd_out: int, fd_stats: int = -1, sw: int = 32768, ops: int = 0) -> int:

@@ -61,6 +61,10 @@ struct dfl_ctx {
     cudaEvent_t *e_in, *e_done;
     unsigned long long *h_totals;     /* pinned: end offset of every piece */
     int pipe_cap;
+    /* fd pipeline (dfl_b200_compress_fd): pinned pieces, device slots */
+    uint8_t *fd_h_in[3], *fd_h_out[2], *fd_d_in[2], *fd_d_out[2];
+    cudaEvent_t fd_e_in[2], fd_e_out[2];
+    size_t fd_piece, fd_piece_req;
     int parse_mode; /* 0 = by segment count, 1 = k_parse_warp, 2 = k_parse */
     int match_mode; /* 0 = k_match_run where the geometry allows, 1 = always k_match */
     int num_sms;
@@ -243,6 +247,8 @@ extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
     return DFL_OK;
 }
 
+static void fd_free(dfl_ctx *ctx);
+
 extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
 {
     if (!ctx) return;
@@ -257,6 +263,7 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     if (ctx->seg_index) cudaFree(ctx->seg_index);
     if (ctx->inf_w) cudaFree(ctx->inf_w);
     if (ctx->d_png) cudaFree(ctx->d_png);
+    fd_free(ctx);
     for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
     free(ctx->e_in); free(ctx->e_done);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
@@ -886,3 +893,5 @@ extern "C" int dfl_b200_png_encode_host(dfl_ctx *ctx, const uint8_t *pix, uint32
     *out_len = total;
     return DFL_OK;
 }
+
+#include "dfl_pipeline.cuh"

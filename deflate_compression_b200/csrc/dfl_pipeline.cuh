@@ -1,0 +1,381 @@
+/* dfl_pipeline.cuh -- host-side pipelines over the device compress call (included at the end of dfl_kernels.cu):
+ *   dfl_b200_compress_fd          fd -> fd, the body of deflate_compress() (src/deflate_compress.c:139-145, :362-376):
+ *                                 reader thread -> pinned pieces -> H2D / kernels / D2H on three streams -> writer thread
+ *   dfl_b200_compress_host_multi  one host thread, N contexts (one per GPU), contiguous shards
+ *   dfl_b200_adler32_combine      Adler-32 of a concatenation from the parts' checksums
+ */
+#pragma once
+
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+#include <errno.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+extern "C" uint32_t dfl_b200_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2)
+{
+    /* both parts started from 1; RFC 1950 section 8.2 arithmetic mod 65521 */
+    const uint64_t M = ADLER_MOD;
+    const uint64_t s1a = a1 & 0xFFFF, s2a = a1 >> 16, s1b = a2 & 0xFFFF, s2b = a2 >> 16;
+    const uint64_t s1 = (s1a + s1b + M - 1) % M;
+    const uint64_t s2 = (s2a + s2b + (len2 % M) * ((s1a + M - 1) % M)) % M;
+    return (uint32_t)((s2 << 16) | s1);
+}
+
+/* ------------------------------------------------------------------------- */
+/* fd -> fd                                                                  */
+/* ------------------------------------------------------------------------- */
+
+#ifndef FD_PIECE_BYTES
+#define FD_PIECE_BYTES (64u << 20) /* one pipeline piece */
+#endif
+#define FD_IN_SLOTS 3  /* pinned input pieces: one being read, one being copied, one being compressed */
+#define FD_OUT_SLOTS 2 /* pinned output pieces: one being filled by the GPU, one being written */
+#define FD_IO_THREADS 8
+
+/* read(2) until n bytes or end of file (fetch(), src/deflate_compress.c:139-145).  A regular file is read by several
+ * threads with pread(2): one thread's copy out of the page cache runs at a third of what the GPU compresses. */
+static long long fd_read_piece(int fd, bool regular, unsigned long long file_off, uint8_t *buf, size_t n)
+{
+    if (regular) {
+        struct stat st;
+        if (fstat(fd, &st) != 0) return -1;
+        const unsigned long long left = (unsigned long long)st.st_size > file_off ? (unsigned long long)st.st_size - file_off : 0;
+        const size_t want = left < n ? (size_t)left : n;
+        if (!want) return 0;
+        const int nt = want >= (8u << 20) ? FD_IO_THREADS : 1;
+        const size_t per = ((want + nt - 1) / nt + 4095) & ~(size_t)4095;
+        bool bad = false;
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) {
+            const size_t lo = (size_t)t * per, hi = lo + per < want ? lo + per : want;
+            if (lo >= hi) break;
+            th.emplace_back([=, &bad] {
+                size_t p = lo;
+                while (p < hi) {
+                    const ssize_t r = pread(fd, buf + p, hi - p, (off_t)(file_off + p));
+                    if (r < 0 && errno == EINTR) continue;
+                    if (r <= 0) { bad = true; return; } /* the file shrank under us, or an I/O error */
+                    p += (size_t)r;
+                }
+            });
+        }
+        for (auto &t : th) t.join();
+        return bad ? -1 : (long long)want;
+    }
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t r = read(fd, buf + got, n - got);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        if (r == 0) break;
+        got += (size_t)r;
+    }
+    return (long long)got;
+}
+
+static int fd_write_all(int fd, const uint8_t *p, size_t n)
+{
+    while (n) {
+        const ssize_t w = write(fd, p, n);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        p += w;
+        n -= (size_t)w;
+    }
+    return 0;
+}
+
+static void fd_free(dfl_ctx *ctx)
+{
+    if (!ctx->fd_h_in[0]) return;
+    for (int i = 0; i < FD_IN_SLOTS; i++) { if (ctx->fd_h_in[i]) cudaFreeHost(ctx->fd_h_in[i]); ctx->fd_h_in[i] = NULL; }
+    for (int i = 0; i < 2; i++) {
+        if (ctx->fd_h_out[i]) cudaFreeHost(ctx->fd_h_out[i]);
+        if (ctx->fd_d_in[i]) cudaFree(ctx->fd_d_in[i]);
+        if (ctx->fd_d_out[i]) cudaFree(ctx->fd_d_out[i]);
+        if (ctx->fd_e_in[i]) cudaEventDestroy(ctx->fd_e_in[i]);
+        if (ctx->fd_e_out[i]) cudaEventDestroy(ctx->fd_e_out[i]);
+        ctx->fd_h_out[i] = ctx->fd_d_in[i] = ctx->fd_d_out[i] = NULL;
+        ctx->fd_e_in[i] = ctx->fd_e_out[i] = NULL;
+    }
+}
+
+extern "C" int dfl_b200_set_fd_piece(dfl_ctx *ctx, size_t bytes)
+{
+    if (!ctx) return DFL_E_INVAL;
+    ctx->fd_piece_req = bytes;
+    return DFL_OK;
+}
+
+namespace {
+struct FdPipe {
+    std::mutex mu;
+    std::condition_variable cv;
+    /* reader -> main: piece i is in h_in[i % FD_IN_SLOTS] with in_len[slot] bytes once in_ready > i; the main thread
+     * frees a slot by raising in_free (pieces whose kernels are done) */
+    long in_ready = 0, in_free = 0;
+    size_t in_len[FD_IN_SLOTS] = {0, 0, 0};
+    bool in_eof = false, in_err = false;
+    /* main -> writer: output piece j is in h_out[j % FD_OUT_SLOTS] with out_len bytes once out_ready > j */
+    long out_ready = 0, out_done = 0;
+    size_t out_len[FD_OUT_SLOTS] = {0, 0};
+    bool out_err = false, out_close = false;
+};
+} // namespace
+
+extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigned long long *in_bytes, unsigned long long *out_bytes)
+{
+    if (!ctx) return DFL_E_INVAL;
+    CK(cudaSetDevice(ctx->device));
+    const dfl_params prm = ctx->prm;
+    size_t piece = (ctx->fd_piece_req ? ctx->fd_piece_req : (size_t)FD_PIECE_BYTES) / (size_t)prm.seg_bytes * (size_t)prm.seg_bytes; /* whole segments */
+    if (piece < (size_t)prm.seg_bytes) piece = (size_t)prm.seg_bytes;
+    if (piece < DFL_MAX_WINDOW) piece = (DFL_MAX_WINDOW + (size_t)prm.seg_bytes - 1) / (size_t)prm.seg_bytes * (size_t)prm.seg_bytes; /* a piece holds the next one's window */
+    const size_t W = DFL_MAX_WINDOW, bound = dfl_b200_bound(&prm, piece) + 16;
+    int rc = host_pipe_init(ctx, 1); /* the three streams */
+    if (rc) return rc;
+    /* pinned host pieces and device slots live with the context */
+    if (ctx->fd_h_in[0] && ctx->fd_piece != piece) fd_free(ctx); /* (piece or segment size changed between calls) */
+    if (!ctx->fd_h_in[0]) {
+        for (int s = 0; s < FD_IN_SLOTS; s++) CK(cudaMallocHost(&ctx->fd_h_in[s], piece));
+        for (int s = 0; s < FD_OUT_SLOTS; s++) CK(cudaMallocHost(&ctx->fd_h_out[s], bound + 16));
+        for (int s = 0; s < 2; s++) {
+            CK(cudaMalloc(&ctx->fd_d_in[s], W + piece + 32));
+            CK(cudaMalloc(&ctx->fd_d_out[s], bound));
+        }
+        for (int s = 0; s < 2; s++) {
+            CK(cudaEventCreateWithFlags(&ctx->fd_e_in[s], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->fd_e_out[s], cudaEventDisableTiming));
+        }
+        ctx->fd_piece = piece;
+    }
+    struct stat st_in;
+    const bool regular = fstat(fd_in, &st_in) == 0 && S_ISREG(st_in.st_mode);
+    unsigned long long start_off = 0;
+    if (regular) {
+        const off_t cur = lseek(fd_in, 0, SEEK_CUR);
+        start_off = cur > 0 ? (unsigned long long)cur : 0;
+    }
+
+    FdPipe P;
+    std::thread reader([&] {
+        unsigned long long off = start_off;
+        for (long i = 0;; i++) {
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                P.cv.wait(lk, [&] { return i - P.in_free < FD_IN_SLOTS || P.out_err; });
+                if (P.out_err) return;
+            }
+            const int s = (int)(i % FD_IN_SLOTS);
+            const long long got = fd_read_piece(fd_in, regular, off, ctx->fd_h_in[s], piece);
+            std::lock_guard<std::mutex> lk(P.mu);
+            if (got < 0) { P.in_err = true; P.in_eof = true; P.cv.notify_all(); return; }
+            off += (unsigned long long)got;
+            P.in_len[s] = (size_t)got;
+            P.in_ready = i + 1;
+            if ((size_t)got < piece) P.in_eof = true;
+            P.cv.notify_all();
+            if ((size_t)got < piece) return;
+        }
+    });
+    std::thread writer([&] {
+        static const uint8_t hdr[2] = {0x78, 0x9C}; /* CM = 8, CINFO = 7, FCHECK: what src/deflate_decompress.c:352-360 checks */
+        bool bad = fd_out >= 0 && fd_write_all(fd_out, hdr, 2) != 0;
+        for (long j = 0;; j++) {
+            size_t len;
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                if (bad) { P.out_err = true; P.cv.notify_all(); }
+                P.cv.wait(lk, [&] { return P.out_ready > j || P.out_close; });
+                if (P.out_ready <= j) return;
+                len = P.out_len[j % FD_OUT_SLOTS];
+            }
+            if (!bad && fd_out >= 0 && fd_write_all(fd_out, ctx->fd_h_out[j % FD_OUT_SLOTS], len) != 0) bad = true;
+            std::lock_guard<std::mutex> lk(P.mu);
+            P.out_done = j + 1;
+            if (bad) P.out_err = true;
+            P.cv.notify_all();
+        }
+    });
+
+    unsigned long long total_in = 0, total_out = 2;
+    uint32_t adler = 1;
+    size_t len_cur = 0, len_next = 0, body_prev = 0;
+    rc = DFL_OK;
+    /* piece i's bytes: the tail of piece i - 1 primes its window (device to device), then the copy in */
+    auto copy_in = [&](long i, size_t len, size_t len_before) -> bool {
+        const int ds = (int)(i & 1);
+        uint8_t *d_piece = ctx->fd_d_in[ds] + W;
+        const size_t hist = i == 0 ? 0 : (len_before < W ? len_before : W);
+        if (hist && cudaMemcpyAsync(d_piece - hist, ctx->fd_d_in[ds ^ 1] + W + len_before - hist, hist, cudaMemcpyDeviceToDevice, ctx->s_in) != cudaSuccess) return false;
+        if (len && cudaMemcpyAsync(d_piece, ctx->fd_h_in[i % FD_IN_SLOTS], len, cudaMemcpyHostToDevice, ctx->s_in) != cudaSuccess) return false;
+        return cudaEventRecord(ctx->fd_e_in[ds], ctx->s_in) == cudaSuccess;
+    };
+    auto wait_piece = [&](long i, size_t *len) -> bool { /* the reader has delivered piece i */
+        std::unique_lock<std::mutex> lk(P.mu);
+        P.cv.wait(lk, [&] { return P.in_ready > i || P.in_err; });
+        if (P.in_err) return false;
+        *len = P.in_len[i % FD_IN_SLOTS];
+        return true;
+    };
+    auto publish = [&](long j, size_t olen) { /* output piece j is complete in its pinned slot: over to the writer */
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.out_len[j % FD_OUT_SLOTS] = olen;
+        P.out_ready = j + 1;
+        P.cv.notify_all();
+    };
+    if (!wait_piece(0, &len_cur)) rc = DFL_E_INVAL;
+    else if (!copy_in(0, len_cur, 0)) rc = DFL_E_CUDA;
+    for (long i = 0; rc == DFL_OK; i++) {
+        const int ds = (int)(i & 1);
+        const size_t len = len_cur, hist = i == 0 ? 0 : (total_in < W ? (size_t)total_in : W);
+        /* a piece that fills its slot may or may not be the last one: the next read tells (it overlapped piece i - 1) */
+        bool last = len < piece;
+        if (!last) {
+            if (!wait_piece(i + 1, &len_next)) { rc = DFL_E_INVAL; break; }
+            last = len_next == 0;
+        }
+        if (cudaStreamWaitEvent(ctx->s_run, ctx->fd_e_in[ds], 0) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+        rc = dfl_b200_deflate_enqueue(ctx, ctx->fd_d_in[ds] + W, len, hist, last ? 1 : 0, ctx->fd_d_out[ds], bound, ctx->s_run);
+        if (rc) break;
+        /* while piece i is compressed: piece i + 1 goes to the device, piece i - 1 goes to the writer */
+        if (!last && !copy_in(i + 1, len_next, len)) { rc = DFL_E_CUDA; break; }
+        if (i > 0) {
+            if (cudaEventSynchronize(ctx->fd_e_out[ds ^ 1]) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+            publish(i - 1, body_prev);
+        }
+        size_t body = 0;
+        uint32_t a = 1;
+        rc = dfl_b200_deflate_finish(ctx, &body, &a, ctx->s_run);
+        if (rc) break;
+        adler = dfl_b200_adler32_combine(adler, a, len);
+        total_in += len;
+        {
+            /* piece i's input slot can be read into again; its output slot must have been written out (two pieces ago) */
+            std::unique_lock<std::mutex> lk(P.mu);
+            P.in_free = i + 1;
+            P.cv.notify_all();
+            P.cv.wait(lk, [&] { return P.out_done >= i - (FD_OUT_SLOTS - 1) || P.out_err; });
+            if (P.out_err) { rc = DFL_E_INVAL; break; }
+        }
+        uint8_t *ho = ctx->fd_h_out[i % FD_OUT_SLOTS];
+        if (body && cudaMemcpyAsync(ho, ctx->fd_d_out[ds], body, cudaMemcpyDeviceToHost, ctx->s_out) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+        if (cudaEventRecord(ctx->fd_e_out[ds], ctx->s_out) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+        total_out += body;
+        body_prev = body;
+        len_cur = len_next;
+        if (last) {
+            if (cudaEventSynchronize(ctx->fd_e_out[ds]) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+            /* RFC 1950: Adler-32 of the uncompressed data, MSB first */
+            ho[body + 0] = (uint8_t)(adler >> 24); ho[body + 1] = (uint8_t)(adler >> 16);
+            ho[body + 2] = (uint8_t)(adler >> 8); ho[body + 3] = (uint8_t)adler;
+            total_out += 4;
+            publish(i, body + 4);
+            break;
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.out_close = true;
+        if (rc) P.out_err = true; /* releases the reader */
+        P.in_free = 1L << 60;
+        P.cv.notify_all();
+    }
+    reader.join();
+    writer.join();
+    if (regular) lseek(fd_in, (off_t)(start_off + total_in), SEEK_SET); /* as read(2) would have left it */
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->s_run);
+    cudaStreamSynchronize(ctx->s_out);
+    if (rc) return rc;
+    if (P.out_err || P.in_err) return DFL_E_INVAL;
+    if (in_bytes) *in_bytes = total_in;
+    if (out_bytes) *out_bytes = total_out;
+    return DFL_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* N GPUs behind one call                                                    */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * The input shards contiguously, one segment-aligned range per context (= per GPU), each primed with the 32 KiB
+ * before it taken from the caller's buffer (no GPU <-> GPU halo), each ended byte aligned by its sync marker; only
+ * the last shard's last block carries BFINAL.  One host thread: every device gets its copy-in and kernels enqueued,
+ * then the bodies come back in rank order straight into the caller's buffer (the offset of shard r is known once
+ * shards 0..r-1 have reported their sizes) and the Adler-32 values are combined.  The copies overlap across devices
+ * when `in` / `out` are pinned (cudaHostRegister / cudaMallocHost); with pageable buffers the result is the same.
+ */
+extern "C" int dfl_b200_compress_host_multi(dfl_ctx **ctxs, int ndev, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                            size_t *out_len)
+{
+    if (!ctxs || ndev < 1 || (!in && n) || !out || !out_len) return DFL_E_INVAL;
+    for (int r = 0; r < ndev; r++)
+        if (!ctxs[r] || memcmp(&ctxs[r]->prm, &ctxs[0]->prm, sizeof(dfl_params)) != 0) return DFL_E_INVAL;
+    const dfl_params prm = ctxs[0]->prm;
+    const size_t nseg = n ? (n + prm.seg_bytes - 1) / prm.seg_bytes : 0;
+    if ((size_t)ndev > nseg) ndev = nseg ? (int)nseg : 1; /* every shard holds at least one segment */
+    if (ndev == 1) return dfl_b200_compress_host(ctxs[0], in, n, out, cap, out_len);
+    const size_t W = (size_t)prm.window;
+    std::vector<size_t> lo(ndev), hi(ndev), hist(ndev);
+    for (int r = 0; r < ndev; r++) {
+        lo[r] = nseg * (size_t)r / (size_t)ndev * (size_t)prm.seg_bytes;
+        hi[r] = nseg * (size_t)(r + 1) / (size_t)ndev * (size_t)prm.seg_bytes;
+        if (lo[r] > n) lo[r] = n;
+        if (hi[r] > n || r == ndev - 1) hi[r] = n;
+        hist[r] = prm.use_dict ? (lo[r] < W ? lo[r] : W) : 0;
+    }
+    /* enqueue everything */
+    for (int r = 0; r < ndev; r++) {
+        dfl_ctx *ctx = ctxs[r];
+        CK(cudaSetDevice(ctx->device));
+        int rc = host_pipe_init(ctx, 1);
+        if (rc) return rc;
+        const size_t len = hi[r] - lo[r];
+        const size_t bound = dfl_b200_bound(&prm, len);
+        { const int rc_ = grow_dev(ctx, &ctx->d_in, &ctx->d_in_cap, W + len + 32); if (rc_) return rc_; }
+        { const int rc_ = grow_dev(ctx, &ctx->d_out, &ctx->d_out_cap, bound + 16); if (rc_) return rc_; }
+        /* the shard sits W bytes into the buffer so that its history lies in front of it, whatever its length */
+        uint8_t *d_shard = ctx->d_in + W;
+        if (hist[r] + len)
+            CK(cudaMemcpyAsync(d_shard - hist[r], in + lo[r] - hist[r], hist[r] + len, cudaMemcpyHostToDevice, ctx->s_run));
+        rc = dfl_b200_deflate_enqueue(ctx, d_shard, len, hist[r], r == ndev - 1, ctx->d_out, bound, ctx->s_run);
+        if (rc) return rc;
+    }
+    /* collect in rank order */
+    size_t pos = 2;
+    uint32_t adler = 1;
+    int rc = DFL_OK;
+    for (int r = 0; r < ndev; r++) {
+        dfl_ctx *ctx = ctxs[r];
+        size_t body = 0;
+        uint32_t a = 1;
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+        rc = dfl_b200_deflate_finish(ctx, &body, &a, ctx->s_run);
+        if (rc) break;
+        if (cap < pos + body + 4) { rc = DFL_E_SZ; break; }
+        if (body && cudaMemcpyAsync(out + pos, ctx->d_out, body, cudaMemcpyDeviceToHost, ctx->s_run) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+        pos += body;
+        adler = dfl_b200_adler32_combine(adler, a, hi[r] - lo[r]);
+    }
+    for (int r = 0; r < ndev; r++) { /* everything in flight lands before the caller's buffers go away */
+        cudaSetDevice(ctxs[r]->device);
+        if (ctxs[r]->s_run && cudaStreamSynchronize(ctxs[r]->s_run) != cudaSuccess && !rc) rc = DFL_E_CUDA;
+    }
+    if (rc) return rc;
+    out[0] = 0x78;
+    out[1] = 0x9C;
+    out[pos + 0] = (uint8_t)(adler >> 24);
+    out[pos + 1] = (uint8_t)(adler >> 16);
+    out[pos + 2] = (uint8_t)(adler >> 8);
+    out[pos + 3] = (uint8_t)adler;
+    *out_len = pos + 4;
+    return DFL_OK;
+}

@@ -148,6 +148,8 @@ static int deflate_compr_run(deflate_compr_t *com)
     int rc;
     dfl_params prm;
     if (com->err) return com->err;
+    /* no record stream wanted: the pipelined fd -> fd path (reads, copies, kernels and writes overlap) */
+    if (com->fd_stats < 0) return map_err(dfl_b200_compress_fd(com->ctx, com->fd_in, com->fd_out, NULL, NULL));
     rc = read_all(com->fd_in, &in, &n);
     if (rc) return rc;
     /* compress_stats.bytes is an int (src/include/deflate_ext.h:20): the record stream cannot describe more */

@@ -120,6 +120,28 @@ int dfl_b200_deflate_finish(dfl_ctx *ctx, size_t *out_len, uint32_t *adler, void
 int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                            size_t *out_len);
 
+/*
+ * fd -> fd, the body of deflate_compress() (src/deflate_compress.c:362-376): everything readable from fd_in
+ * (read(2) until it returns 0, :139-145; a regular file is read with pread(2) by several threads) becomes a zlib
+ * stream on fd_out (-1: discarded).  A reader thread fills pinned pieces of 64 MiB, the copy in, the kernels and
+ * the copy out of neighbouring pieces overlap on three streams, a writer thread empties the pinned output
+ * pieces; the stream is byte-identical to dfl_b200_compress_host's on the same bytes.
+ */
+int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigned long long *in_bytes, unsigned long long *out_bytes);
+int dfl_b200_set_fd_piece(dfl_ctx *ctx, size_t bytes); /* piece size of the fd pipeline (0 = 64 MiB); test support */
+
+/*
+ * N GPUs behind one call: ctxs[r] is a context on GPU r, all with the same parameters.
+ * in[0, n) shards contiguously into segment-aligned ranges, one per context, each primed with the 32 KiB before
+ * it; the bodies land in rank order in out, after the zlib header and before the combined Adler-32.  One host
+ * thread drives all devices; the stream equals dfl_b200_compress_host's on one GPU.  Pinned in / out buffers let
+ * the copies of different devices overlap.
+ */
+int dfl_b200_compress_host_multi(dfl_ctx **ctxs, int ndev, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                 size_t *out_len);
+/* Adler-32 of a concatenation A | B from adler32(A), adler32(B) (both from start value 1) and len(B). */
+uint32_t dfl_b200_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);
+
 /* Parity / fd_stats support: keep the token stream of the next compress calls
  * on the host (4 bytes per input byte).  Token = literal byte, or dist<<16|len. */
 int dfl_b200_keep_tokens(dfl_ctx *ctx, int enable);

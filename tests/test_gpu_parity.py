@@ -180,6 +180,79 @@ def test_fd_api_roundtrip(D, O, tmp_path):
     assert k == recs.shape[0]
 
 
+@pytest.mark.parametrize("n,piece", [(0, 0), (1, 0), (70000, 0), (3 * 65536, 65536), (3 * 65536 + 1, 65536), (5 * 65536 - 7, 65536),
+                                     (1000003, 131072), (40 << 20, 8 << 20)])
+def test_fd_pipeline_matches_whole_buffer(D, O, tmp_path, n, piece):
+    """dfl_b200_compress_fd (reader thread, pinned pieces, three streams, writer thread) writes the stream the
+    whole-buffer call writes -- pieces are whole segments primed with the 32 KiB before them -- for inputs that
+    end inside a piece, exactly on a piece boundary, and for an empty input; regular files (pread by several
+    threads) and pipes (read until 0)."""
+    data = make_input("markov", 91, 0, n) if n else np.zeros(0, dtype=np.uint8)
+    comp = D.Compressor()
+    want = comp.compress(data)
+    if n <= 1000003:
+        assert want == O.zlib_compress(data, O.params())
+    src, dst = tmp_path / "in", tmp_path / "out.z"
+    src.write_bytes(data.tobytes())
+    fi, fo = os.open(src, os.O_RDONLY), os.open(dst, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    try:
+        nin, nout = comp.compress_fd(fi, fo, piece)
+        assert os.lseek(fi, 0, os.SEEK_CUR) == n  # the offset is where read(2) would have left it
+    finally:
+        os.close(fi), os.close(fo)
+    assert (nin, nout) == (n, len(want))
+    assert dst.read_bytes() == want
+    # the same through pipes, fed and drained by threads
+    import threading
+
+    r_in, w_in = os.pipe()
+    r_out, w_out = os.pipe()
+    got = bytearray()
+
+    def feed():
+        view = memoryview(data.tobytes())
+        pos = 0
+        while pos < len(view):
+            pos += os.write(w_in, view[pos:pos + (1 << 20)])
+        os.close(w_in)
+
+    def drain():
+        while True:
+            b = os.read(r_out, 1 << 20)
+            if not b:
+                break
+            got.extend(b)
+
+    tf, td = threading.Thread(target=feed), threading.Thread(target=drain)
+    tf.start(), td.start()
+    try:
+        nin, nout = comp.compress_fd(r_in, w_out, piece)
+    finally:
+        os.close(w_out)
+        tf.join(), td.join()
+        os.close(r_in), os.close(r_out)
+    assert (nin, nout) == (n, len(want)) and bytes(got) == want
+    comp.close()
+
+
+def test_compress_host_multi_one_gpu_many_contexts(D, O):
+    """dfl_b200_compress_host_multi with several contexts (all on GPU 0 here; one per GPU in bench.py --gpus N):
+    contiguous segment-aligned shards, each primed with the 32 KiB before it, bodies in rank order, Adler-32
+    combined in C -- the stream is the single-context stream."""
+    for n, k in ((0, 3), (5, 2), (32768 * 3, 4), (700001, 3), (2000003, 8), (100, 5)):
+        data = make_input("markov", 92, 0, n) if n else np.zeros(0, dtype=np.uint8)
+        comps = [D.Compressor() for _ in range(k)]
+        cap = comps[0].bound(n) + 64
+        out = np.empty(cap, dtype=np.uint8)
+        z_len = D.compress_multi(comps, data.ctypes.data if n else 0, n, out.ctypes.data, cap)
+        z = out[:z_len].tobytes()
+        assert z == O.zlib_compress(data, O.params()), (n, k)
+        assert zlib.decompress(z) == data.tobytes()
+        for c in comps:
+            c.close()
+    assert D.lib().dfl_b200_adler32_combine(O.adler32(b"abc"), O.adler32(b"defgh"), 5) == O.adler32(b"abcdefgh")
+
+
 def test_fd_api_pipe_and_errors(D):
     r, w = os.pipe()
     os.write(w, b"hello hello hello hello")
