@@ -132,11 +132,6 @@ def lib() -> C.CDLL:
         L.spawn_deflate_compr_t.restype = vp
         L.deflate_compr_init.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_ushort]
         L.deflate_compr_deinit.argtypes = [vp]
-        # synthetic corpora (host)
-        L.dfl_synth_random.argtypes = [vp, C.c_size_t, C.c_uint64]
-        L.dfl_synth_markov.argtypes = [vp, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint32]
-        L.dfl_synth_log.argtypes = [vp, C.c_size_t, C.c_uint64, vp, C.c_size_t]
-        L.dfl_synth_png.argtypes = [vp, C.c_size_t, C.c_uint64]
         _lib = L
     return _lib
 

@@ -45,9 +45,9 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
     int st = ST_IDLE;
     int i = 0, p = 0, q = 0, k = 0, k_lo = 0, k_hi = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
     uint32_t pw0 = 0, pw1 = 0, fword = 0, fmask = 0;
-    uint32_t lb = lbase; /* list a TWO-list walk is in */
-    uint32_t ow = 0;     /* TWO: the bucket's range in the window block's list */
+    uint32_t ow = 0;     /* TWO: the bucket's range in the window block's list (slots relative to RUN_BLK); OW_DONE once the walk is in it */
     int foff = 0;
+    constexpr uint32_t OW_DONE = 0xFFFFFFFFu; /* (no bucket ends at slot 65535 and starts at 65535) */
     (void)hops; (void)ow; (void)lbase_old;
 
     /* take position i_ as a parse head (caller has claimed it) */
@@ -66,7 +66,7 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 pw1 = ld4s(dbase + p + 4);                                              \
                 foff = 0; fmask = fmask0; fword = pw0 & fmask0;                         \
                 const uint32_t b_ = hash4(pw0, ngrp, sb);                               \
-                if (TWO) { ow = __ldcg(oo + b_); lb = lbase; }                          \
+                if (TWO) ow = __ldcg(oo + b_);                                                                    \
                 k_lo = (int)lds_u16(obase + 2 * b_);                                    \
                 k = k_lo;                                                               \
                 k_hi = (int)lds_u16(obase + 2 * b_ + 2);                                \
@@ -102,25 +102,23 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
             } else {
 #pragma unroll 1
                 for (int t = 0; t < HOP_BATCH; t += 2) {
-                    int q1, q2, real2 = 0;
-                    if (!TWO) {
-                        if (k <= k_lo) { st = ST_DONE; break; }
-                        q1 = (int)lds_u16(lbase + 2 * (k - 1));
-                        q2 = k - 1 > k_lo ? (int)lds_u16(lbase + 2 * (k - 2)) : p - W - 1; /* no second entry: reads as "outside the window" */
-                        real2 = 1; /* (k is only looked at again when q2 was a real entry) */
+                    int q1, q2, real2 = 1; /* real2: q2 is a bucket entry (k is only looked at again then) */
+                    if (k - k_lo >= 2) { /* both entries come from the list the walk is in */
+                        q1 = (int)lds_u16(lbase + 2 * k - 2);
+                        q2 = (int)lds_u16(lbase + 2 * k - 4);
                         k -= 2;
                     } else {
-                        /* the next two entries of the bucket, nearest first: the segment block's list, then the window
-                         * block's (the hand-over happens between any two entries, no step is lost to it) */
+                        /* at the end of a list: one entry left, or none.  TWO: the segment block's list is followed by
+                         * the window block's, the hand-over happens between any two entries (no step is lost to it) */
                         if (k <= k_lo) {
-                            if (lb != lbase) { st = ST_DONE; break; }
-                            lb = lbase_old; k_lo = (int)(ow & 0xFFFF); k = (int)(ow >> 16);
+                            if (!TWO || ow == OW_DONE) { st = ST_DONE; break; }
+                            k_lo = RUN_BLK + (int)(ow & 0xFFFF); k = RUN_BLK + (int)(ow >> 16); ow = OW_DONE;
                             if (k <= k_lo) { st = ST_DONE; break; }
                         }
-                        q1 = (int)lds_u16(lb + 2 * (--k));
-                        if (k <= k_lo && lb == lbase) { lb = lbase_old; k_lo = (int)(ow & 0xFFFF); k = (int)(ow >> 16); }
-                        q2 = p - W - 1;
-                        if (k > k_lo) { q2 = (int)lds_u16(lb + 2 * (--k)); real2 = 1; }
+                        q1 = (int)lds_u16(lbase + 2 * (--k));
+                        if (TWO && k <= k_lo && ow != OW_DONE) { k_lo = RUN_BLK + (int)(ow & 0xFFFF); k = RUN_BLK + (int)(ow >> 16); ow = OW_DONE; }
+                        if (k > k_lo) q2 = (int)lds_u16(lbase + 2 * (--k));
+                        else { q2 = p - W - 1; real2 = 0; } /* no second entry: reads as "outside the window" */
                     }
                     const uint32_t w1 = ld4s(dbase + q1 + foff), w2 = ld4s(dbase + (q2 < 0 ? 0 : q2) + foff);
 #ifdef DFL_SEARCH_STATS
@@ -145,7 +143,10 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
             int rem = k - k_lo;
             if (HAS_K && K - hops < rem) rem = K - hops;
             /* TWO: the window block's part counts too, by the share of that block the head's window still covers */
-            if (TWO && lb == lbase) rem += (int)(((ow >> 16) - (ow & 0xFFFF)) * (uint32_t)(RUN_BLK - i)) >> 15;
+            #ifndef REM_SCALED
+#define REM_SCALED 1
+#endif
+            if (TWO && ow != OW_DONE) rem += REM_SCALED ? (int)(((ow >> 16) - (ow & 0xFFFF)) * (uint32_t)(RUN_BLK - i)) >> 15 : (int)((ow >> 16) - (ow & 0xFFFF));
             if (rem > COOP_MIN) st = ST_HEAVY;
         }
         /* phase B: full compare (check_dup_str) for the lanes holding a candidate.  A lane compares up
@@ -229,7 +230,7 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 int hlo = __shfl_sync(FULL, k_lo, L);
                 const int hmax = __shfl_sync(FULL, maxlen, L);
                 const uint32_t hw0 = __shfl_sync(FULL, pw0, L), hw1 = __shfl_sync(FULL, pw1, L);
-                const uint32_t hlb = TWO ? __shfl_sync(FULL, lb, L) : lbase;
+                const uint32_t how = TWO ? __shfl_sync(FULL, ow, L) : 0u;
                 const int hhops = HAS_K ? __shfl_sync(FULL, hops, L) : 0;
                 if (HAS_K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
                 int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
@@ -237,19 +238,17 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 uint32_t hfmask = hbest == 2 ? fmask0 : 0xFFFFFFFFu;
                 uint32_t hfword = ld4s(dbase + hp + hfoff) & hfmask;
                 bool ended = false; /* the walk is over: best == maxlen, or the rest of the bucket is outside the window */
-                uint32_t hlb_ = hlb;
                 int hk_ = hk, hlo_ = hlo;
 #pragma unroll 1
                 for (int part = 0; part < (TWO ? 2 : 1) && !ended; part++) {
                     if (TWO && part == 1) { /* then the window block's part of the bucket */
-                        if (hlb != lbase) break;
-                        const uint32_t how = __shfl_sync(FULL, ow, L);
-                        hlb_ = lbase_old; hk_ = (int)(how >> 16); hlo_ = (int)(how & 0xFFFF);
+                        if (how == OW_DONE) break;
+                        hk_ = RUN_BLK + (int)(how >> 16); hlo_ = RUN_BLK + (int)(how & 0xFFFF);
                     }
                     for (int top = hk_; top > hlo_; top -= 32) {
                         const int kk = top - 1 - lane;
                         bool valid = kk >= hlo_;
-                        const int cq = valid ? (int)lds_u16(hlb_ + 2 * kk) : 0;
+                        const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
                         valid = valid && (hp - cq <= W);
                         uint32_t key = valid ? 0x80000000u : 0u;
                         if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {

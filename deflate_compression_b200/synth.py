@@ -5,19 +5,39 @@ committed table data/markov2.npz (made by data/make_markov_model.py from the
 reference's sample text).  Nothing here touches /root/reference."""
 from __future__ import annotations
 
+import ctypes as C
 import os
+import subprocess
 
 import numpy as np
 
-from . import api
-
+PKG = os.path.dirname(os.path.abspath(__file__))
 _MODEL = None
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    """libdfl_synth.so: the host generators (csrc/host/synth.c), a library of their own so that generating a
+    corpus -- the reference arm of bench.py does -- never loads the product library."""
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(PKG, "libdfl_synth.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", os.path.join(PKG, "csrc"), "-s", path], check=True)
+        L = C.CDLL(path)
+        vp = C.c_void_p
+        L.dfl_synth_random.argtypes = [vp, C.c_size_t, C.c_uint64]
+        L.dfl_synth_markov.argtypes = [vp, C.c_size_t, C.c_uint64, vp, vp, vp, C.c_uint32]
+        L.dfl_synth_log.argtypes = [vp, C.c_size_t, C.c_uint64, vp, C.c_size_t]
+        L.dfl_synth_png.argtypes = [vp, C.c_size_t, C.c_uint64]
+        _LIB = L
+    return _LIB
 
 
 def _model():
     global _MODEL
     if _MODEL is None:
-        z = np.load(os.path.join(api.PKG, "data", "markov2.npz"))
+        z = np.load(os.path.join(PKG, "data", "markov2.npz"))
         ctx = z["ctx"].astype(np.int64)
         cnt = z["cnt"].astype(np.int64)
         ctx_off = np.zeros(65537, dtype=np.uint32)
@@ -32,7 +52,7 @@ def _model():
 
 def random_bytes(n: int, seed: int) -> np.ndarray:
     out = np.empty(n, dtype=np.uint8)
-    api.lib().dfl_synth_random(out.ctypes.data, n, seed)
+    lib().dfl_synth_random(out.ctypes.data, n, seed)
     return out
 
 
@@ -40,7 +60,7 @@ def markov(n: int, seed: int) -> np.ndarray:
     """Order-2 Markov 'English-like' text (configs 1 and 2: seeds 1 and 2)."""
     ctx_off, nxt, cum, start = _model()
     out = np.empty(n, dtype=np.uint8)
-    api.lib().dfl_synth_markov(out.ctypes.data, n, seed, ctx_off.ctypes.data, nxt.ctypes.data, cum.ctypes.data, start)
+    lib().dfl_synth_markov(out.ctypes.data, n, seed, ctx_off.ctypes.data, nxt.ctypes.data, cum.ctypes.data, start)
     return out
 
 
@@ -48,14 +68,14 @@ def log(n: int, seed: int = 3) -> np.ndarray:
     """Highly repetitive log lines (config 3)."""
     text = markov(64 * 300 + 300, seed)
     out = np.empty(n, dtype=np.uint8)
-    api.lib().dfl_synth_log(out.ctypes.data, n, seed, text.ctypes.data, text.size)
+    lib().dfl_synth_log(out.ctypes.data, n, seed, text.ctypes.data, text.size)
     return out
 
 
 def png_rows(n: int, seed: int = 6) -> np.ndarray:
     """PNG-style filtered RGB scanlines (config 5)."""
     out = np.empty(n, dtype=np.uint8)
-    api.lib().dfl_synth_png(out.ctypes.data, n, seed)
+    lib().dfl_synth_png(out.ctypes.data, n, seed)
     return out
 
 

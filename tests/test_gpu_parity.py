@@ -253,6 +253,22 @@ def test_compress_host_multi_one_gpu_many_contexts(D, O):
     assert D.lib().dfl_b200_adler32_combine(O.adler32(b"abc"), O.adler32(b"defgh"), 5) == O.adler32(b"abcdefgh")
 
 
+@pytest.mark.parametrize("kind,seed,n", [("markov", 2, 200000), ("log", 3, 150000), ("random", 4, 70000), ("markov", 2, 2)])
+def test_check_lld_target(D, tmp_path, kind, seed, n):
+    """`make check_lld` (the reference's test target, Makefile:26-27): a C program compiled against
+    include/deflate_ext.h that forks, compresses in the child and, in the parent, expands the compress_stats
+    records (tests/check_lld.c:20-54) and inflates the stream; exit status 0 iff both give the file back."""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(D.lib_path()), "check_lld")
+    assert os.path.exists(exe)
+    src = tmp_path / "in"
+    src.write_bytes(make_input(kind, seed, 0, n).tobytes())
+    r = subprocess.run([exe, str(src)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.startswith("check_lld ok: %d bytes" % n)
+
+
 def test_fd_api_pipe_and_errors(D):
     r, w = os.pipe()
     os.write(w, b"hello hello hello hello")

@@ -6,4 +6,4 @@ name=$1; shift
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Iinclude "$@" \
   -Wno-deprecated-gpu-targets -c deflate_compression_b200/csrc/dfl_kernels.cu -o build_variants/$name.o
 nvcc -shared -o build_variants/libdfl_$name.so build_variants/$name.o deflate_compression_b200/csrc/build/deflate_compress.o \
-  deflate_compression_b200/csrc/build/deflate_decompress.o deflate_compression_b200/csrc/build/synth.o -lcudart -Wno-deprecated-gpu-targets
+  deflate_compression_b200/csrc/build/deflate_decompress.o -lcudart -Wno-deprecated-gpu-targets

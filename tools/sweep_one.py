@@ -14,7 +14,7 @@ def run(data, **prm):
         best = min(best, comp.kernel_ms()["k_match"])
     ph = comp.phase_cycles(); nseg = data.size // 32768
     return best, ph["build"] / nseg, ph["search"] / nseg, ph["plain_segments"] / nseg
-n = 64 << 20
+n = int(os.environ.get("SWEEP_MB", "64")) << 20
 res = []
 for name, data, prm in (("text", synth.markov(n, 2), {}), ("text_k16", synth.markov(n, 2), dict(chain_limit=16)), ("log", synth.log(n, 3), {}), ("png", synth.png_rows(n, 6), {}), ("rand", synth.random_bytes(n, 4), {}), ("zeros", np.zeros(n, dtype=np.uint8), {})):
     ms, b, s, pl = run(data, **prm)
