@@ -16,6 +16,12 @@ and compressed bytes to rank 0 with NCCL; the transfer of step k runs while the
 kernels of step k + 1 do (two output buffers), and the clock stops only after the
 last step's bytes have arrived.
 
+After the timed region the same line gets `other_workloads` (one device-timed pass each of BASELINE configs 3, 4
+and 5: 1 GiB log lines, 4 GiB random bytes generated on the device, and this rank's share of the 16 GiB mixed
+text / PNG-scanline corpus), `e2e_fd` (the reference entry point itself, deflate_compress(fd_in, fd_out, -1, 32768,
+0) over memfds) and, for every N, `roundtrip_ok`: the bytes the timed loop wrote (gathered on rank 0 for N > 1,
+stitched with the combined Adler-32) are inflated with zlib and compared with the corpus.
+
 `--impl reference` times the reference's own CPU implementation of the path
 (oracle/_ref/libref.so, the unmodified reference LZ77 loop, on independent
 32 KiB slices) on all host cores; the default arm also times it single-threaded
@@ -43,6 +49,10 @@ TEXT_SEED = 2                    # configs[1]: seed 2
 WINDOW = 32768
 CPU_SAMPLE = 16 << 20            # cpu_baseline sample (single thread)
 REF_STEP_SAMPLE = 64 << 20       # --impl reference: bytes per step, all cores
+LOG_BYTES = 1 << 30              # configs[2]
+RANDOM_BYTES = 4 << 30           # configs[3]
+MIXED_BYTES = 16 << 30           # configs[4], split over the ranks
+MIXED_SEEDS = 4                  # distinct stripes per kind; the corpus cycles through them (a stripe is 1000 windows long)
 
 
 def corpus(lo: int, hi: int) -> np.ndarray:
@@ -117,13 +127,45 @@ def measured_peak() -> tuple[float, str]:
 
 
 def ncu_traffic(n_in: int) -> float | None:
-    """dram bytes (read + write) per k_match launch from the committed ncu capture, scaled to this launch size."""
+    """dram bytes (read + write) of the dominant kernel's launch, from the committed ncu capture of this command's own
+    256 MiB launch (profiles/r02_k_match_traffic.json; null when the capture was taken at another launch size)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k_match_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_k_match_traffic.json")) as f:
             j = json.load(f)
-        return float(j["dram_bytes_per_input_byte"]) * n_in
+        return float(j["dram_bytes_per_launch"]) if int(j["launch_input_bytes"]) == n_in else None
     except Exception:
         return None
+
+
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus near gpu {index}"
+    except Exception as e:  # no NVML, one NUMA node, or a restricted cpuset: run where we are
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
+def mixed_shard(lo: int, hi: int):
+    """[lo - hist, hi) of config 5's corpus as (list of (kind, seed index, offset in stripe, length), hist): alternating 32 MiB
+    stripes of Markov text and filtered scanlines; the stripes of a kind cycle through MIXED_SEEDS seeds."""
+    hist = min(lo, WINDOW)
+    parts, pos = [], lo - hist
+    while pos < hi:
+        k = pos // STRIPE
+        end = min(hi, (k + 1) * STRIPE)
+        parts.append((k % 2, (k // 2) % MIXED_SEEDS, pos - k * STRIPE, end - pos))
+        pos = end
+    return parts, hist
 
 
 # --------------------------------------------------------------------------- reference arm / cpu baseline
@@ -148,6 +190,8 @@ def cpu_reference_throughput(sample: np.ndarray, procs: int, repeat: int = 1):
     from oracle import pyoracle as O
 
     kind = "reference" if O.have_ref() else "port"
+    if O.have_ref():
+        O.ref()  # loaded here, before the pool forks: the workers inherit oracle/_ref/libref.so
     with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
         np.save(f, sample)
         path = f.name
@@ -198,15 +242,136 @@ def run_reference(args) -> None:
 
 # --------------------------------------------------------------------------- GPU arm
 
+def device_pass(comp, d_in: int, n: int, hist: int, is_final: bool, d_out, cap: int, stream: int, reps: int = 2):
+    """`reps` device-timed passes of the whole path over one resident input; returns the last one's (ms, out_len, adler, kernel ms)."""
+    import torch
+
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        comp.enqueue(d_in, n, hist, is_final, d_out.data_ptr(), cap, stream)
+        e1.record()
+        out_len, adler = comp.finish(stream)
+        torch.cuda.synchronize()
+        best = (e0.elapsed_time(e1), out_len, adler, comp.kernel_ms())
+    return best
+
+
+def other_workloads(D, comp, dev, rank: int, world: int, stream: int, dist, peak: float) -> dict:
+    """One device-timed pass (after one warm pass) each of BASELINE configs 3, 4 and 5, with the device round trip
+    (segment-parallel inflate, compared on the device) of what the pass wrote."""
+    import torch
+
+    from deflate_compression_b200 import synth
+
+    res = {}
+
+    def roundtrip(d_buf, hist, n, d_out, out_len, adler):
+        d_off = torch.from_numpy(comp.seg_index().astype(np.int64)).to(dev)
+        d_back = torch.empty(hist + n, dtype=torch.uint8, device=dev)
+        d_back[:hist].copy_(d_buf[:hist])
+        a2 = comp.inflate_device(d_out.data_ptr(), out_len, d_off.data_ptr(), (n + 32767) // 32768, d_back.data_ptr() + hist, n, hist, stream)
+        ok = bool(a2 == adler) and bool(torch.equal(d_back[hist:], d_buf[hist:hist + n]))
+        del d_back, d_off
+        return ok
+
+    def run(name, d_buf, hist, n, is_final, what):
+        cap = comp.bound(n)
+        d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        ms, out_len, adler, k = device_pass(comp, d_buf.data_ptr() + hist, n, hist, is_final, d_out, cap, stream)
+        ok = roundtrip(d_buf, hist, n, d_out, out_len, adler)
+        t = torch.tensor([ms, k["k_match"], 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(n), float(out_len)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        ms, km, bad = t.tolist()
+        n_tot, out_tot = tot.tolist()
+        res[name] = {"workload": what, "value": n_tot / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ms, "input_bytes": int(n_tot),
+                     "ratio": n_tot / out_tot, "kernel_ms": {a: round(b, 3) for a, b in k.items() if b},
+                     "roofline": {"bound": "hbm", "kernel": "k_match", "frac": (n + out_len) / (km * 1e-3) / 1e9 / peak,
+                                  "path_frac": (n_tot + out_tot) / world / (ms * 1e-3) / 1e9 / peak},
+                     "roundtrip_ok": bad == 0.0}
+        del d_out
+        torch.cuda.empty_cache()
+
+    # config 3: every rank takes the same 1 GiB of log lines (a replica, not a shard: the config is a 1-GPU one)
+    d_log = torch.from_numpy(synth.log(LOG_BYTES, 3)).to(dev)
+    run("log", d_log, 0, LOG_BYTES, True, "1 GiB repetitive log lines per GPU (BASELINE configs[2], seed 3)")
+    del d_log
+    # config 4: splitmix64 bytes generated on the device
+    d_rnd = torch.empty(RANDOM_BYTES, dtype=torch.uint8, device=dev)
+    D.lib().dfl_b200_synth_random(d_rnd.data_ptr(), RANDOM_BYTES, 4 + rank, stream)
+    torch.cuda.synchronize()
+    run("random", d_rnd, 0, RANDOM_BYTES, True, "4 GiB splitmix64 bytes per GPU, generated on the device (BASELINE configs[3], seed 4 + rank)")
+    del d_rnd
+    torch.cuda.empty_cache()
+    # config 5: this rank's contiguous share of the 16 GiB mixed corpus (2 GiB of it on a single GPU)
+    total = MIXED_BYTES if world > 1 else 2 << 30
+    lo, hi = rank * (total // world), (rank + 1) * (total // world)
+    parts, hist = mixed_shard(lo, hi)
+    stripes = {}
+    d_mix = torch.empty(hist + hi - lo, dtype=torch.uint8, device=dev)
+    pos = 0
+    for kind, sd, off, ln in parts:
+        if (kind, sd) not in stripes:
+            gen = synth.markov if kind == 0 else synth.png_rows
+            stripes[(kind, sd)] = torch.from_numpy(gen(STRIPE, (5 if kind == 0 else 6) * 1000003 + sd)).to(dev)
+        d_mix[pos:pos + ln].copy_(stripes[(kind, sd)][off:off + ln])
+        pos += ln
+    del stripes
+    run("mixed", d_mix, hist, hi - lo, rank == world - 1,
+        f"{total >> 30} GiB mixed corpus over {world} GPU(s): alternating 32 MiB stripes of Markov text and PNG-filtered RGB "
+        f"scanlines cycling through {MIXED_SEEDS} seeds per kind, contiguous shards (BASELINE configs[4])")
+    del d_mix
+    torch.cuda.empty_cache()
+    return res
+
+
+def e2e_fd_throughput(D, host_bytes: np.ndarray, reps: int = 3):
+    """GB/s of the reference entry point itself: deflate_compress(fd_in, fd_out, -1, 32768, 0) over memfds."""
+    fi, fo = os.memfd_create("dfl_in"), os.memfd_create("dfl_out")
+    try:
+        view = memoryview(host_bytes)
+        pos = 0
+        while pos < len(view):
+            pos += os.write(fi, view[pos:pos + (64 << 20)])
+        times, size = [], 0
+        for _ in range(reps + 1):
+            os.lseek(fi, 0, os.SEEK_SET)
+            os.ftruncate(fo, 0)
+            os.lseek(fo, 0, os.SEEK_SET)
+            t0 = time.perf_counter()
+            rc = D.deflate_compress(fi, fo, -1, 32768, 0)
+            times.append(time.perf_counter() - t0)
+            if rc:
+                return None, None, rc
+            size = os.lseek(fo, 0, os.SEEK_CUR)
+        os.lseek(fo, 0, os.SEEK_SET)
+        z = os.read(fo, size)
+        while len(z) < size:
+            z += os.read(fo, size - len(z))
+        return host_bytes.size / min(times[1:]) / 1e9, z, 0
+    finally:
+        os.close(fi), os.close(fo)
+
+
 def run_gpu(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    binding = bind_to_gpu_numa_node(local)  # before anything is allocated: pinned buffers are first-touched here
+    if world > 1:
+        # the gather's transfers go through the copy engines: NCCL's send/recv kernels would take SMs from a kernel that
+        # runs one CTA per SM (measured in round 1: 5 % of the 8-GPU device-timed throughput)
+        os.environ.setdefault("NCCL_P2P_USE_CUDA_MEMCPY", "1")
+
     import torch
     import torch.distributed as dist
 
     import deflate_compression_b200 as D
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -233,6 +398,7 @@ def run_gpu(args) -> None:
     if world > 1 and rank == 0:
         gather_bufs = [torch.empty(world * cap, dtype=torch.uint8, device=dev) for _ in range(2)]
     pending = [None, None]
+    last_gather = {}
 
     def drain(b=None):
         for k in ((0, 1) if b is None else (b,)):
@@ -249,16 +415,18 @@ def run_gpu(args) -> None:
         comp.enqueue(d_in, n, hist, is_final, d_outs[b].data_ptr(), cap, stream)
         out_len, adler = comp.finish(stream)
         if world > 1 and with_gather:
-            sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-            mine = torch.tensor([out_len], dtype=torch.int64, device=dev)
+            sizes = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+            mine = torch.tensor([out_len, adler], dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(sizes, mine)
-            sz = sizes.tolist()
+            meta = sizes.tolist()
+            sz = meta[0::2]
             if rank == 0:
                 offs = np.concatenate([[0], np.cumsum(sz)])
                 gbuf = gather_bufs[b]
                 gbuf[:sz[0]].copy_(d_outs[b][:sz[0]])
                 ops = [dist.P2POp(dist.irecv, gbuf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
                 pending[b] = dist.batch_isend_irecv(ops)
+                last_gather.update(buf=b, sizes=sz, adlers=meta[1::2])
             else:
                 pending[b] = dist.batch_isend_irecv([dist.P2POp(dist.isend, d_outs[b][:out_len], 0)])
         return out_len, adler
@@ -292,6 +460,48 @@ def run_gpu(args) -> None:
     ms = e0.elapsed_time(e1)
     launches = comp.kernel_launches() - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    kernel_ms = comp.kernel_ms()
+    timed_buf = (args.steps - 1) & 1 if world > 1 else 0   # the buffer the last timed step wrote
+
+    # ---- what the timed loop produced, checked outside the timed region ----
+    import hashlib
+    import zlib
+
+    digest = hashlib.blake2b(host[hist:].tobytes(), digest_size=16).digest()
+    roundtrip_ok, roundtrip_what = None, None
+    if world == 1:
+        timed_body = d_outs[0][:out_len].cpu().numpy().tobytes()
+        timed_stream = b"\x78\x9c" + timed_body + int(adler).to_bytes(4, "big")
+        roundtrip_ok = zlib.decompress(timed_stream) == host[hist:].tobytes()
+        roundtrip_what = "zlib.decompress(header + the body the last timed step left in HBM + its Adler-32) == the corpus"
+    else:
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+        if rank == 0:
+            from deflate_compression_b200 import shard
+
+            sz, b = last_gather["sizes"], last_gather["buf"]
+            body = gather_bufs[b][:sum(sz)].cpu().numpy().tobytes()
+            offs = np.concatenate([[0], np.cumsum(sz)])
+            z = shard.stitch([body[int(offs[r]):int(offs[r + 1])] for r in range(world)], last_gather["adlers"], [SHARD_BYTES] * world)
+            del body
+            dec = zlib.decompressobj()
+            ok, pos, h, got = True, 0, hashlib.blake2b(digest_size=16), 0
+            for c0 in range(0, len(z), 8 << 20):
+                out = dec.decompress(z[c0:c0 + (8 << 20)])
+                view = memoryview(out)
+                while len(view):
+                    take = min(len(view), SHARD_BYTES - got)
+                    h.update(view[:take])
+                    got += take
+                    view = view[take:]
+                    if got == SHARD_BYTES:
+                        ok = ok and pos < world and h.digest() == digests[pos]
+                        pos, h, got = pos + 1, hashlib.blake2b(digest_size=16), 0
+            roundtrip_ok = bool(ok and dec.eof and pos == world and got == 0)   # (zlib has checked the combined Adler-32)
+            roundtrip_what = (f"the {world} bodies gathered on rank 0 by the last timed step, stitched with the combined Adler-32, "
+                              "inflate with zlib to the shards (per-shard BLAKE2b digests from their ranks)")
+            del z
 
     # compress-only (no gather) for N > 1
     ms_nogather = ms
@@ -317,6 +527,19 @@ def run_gpu(args) -> None:
         z_len = comp_h.compress_into(h_in.data_ptr(), n, h_out.data_ptr(), cap + 16)
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
+    e2e_stream = h_out[:z_len].numpy().tobytes()
+    e2e_ok = zlib.decompress(e2e_stream) == host[hist:].tobytes() if rank == 0 and world == 1 else None
+    if world == 1:
+        # the device-timed leg and the end-to-end leg wrote the same body
+        roundtrip_ok = bool(roundtrip_ok and e2e_stream[2:-4] == timed_body)
+    comp_h.close()
+    del h_out
+
+    # ---- the reference entry point itself: deflate_compress(fd_in, fd_out, -1, 32768, 0) over memfds ----
+    sync()
+    os.environ["DFL_B200_DEVICE"] = str(local)  # the entry point has no device argument
+    fd_gbs, fd_stream, fd_rc = e2e_fd_throughput(D, host[hist:])
+    fd_ok = bool(fd_stream is not None and zlib.decompress(fd_stream) == host[hist:].tobytes()) if rank == 0 else None
 
     # ---- the way back: segment-parallel inflate of what the timed step wrote, device to
     # device, compared with the shard on the device.  Not part of `value`; reported beside it. ----
@@ -333,25 +556,26 @@ def run_gpu(args) -> None:
         inf_ms.append(k["k_inflate"] + k["k_inf_resolve"] + k["k_inf_finish"])
     inflate_ok = bool(adler_back == adler) and bool(torch.equal(d_back[hist:], d_buf[hist:]))
     inflate_rounds = comp.inflate_rounds()
-    comp.enqueue(d_in, n, hist, is_final, d_out.data_ptr(), cap, stream)  # leave the per-kernel times of a compress step behind
-    comp.finish(stream)
+    del d_back, d_off
 
     # ---- reduce over ranks: max time ----
-    t = torch.tensor([ms, ms_nogather, te * 1e3, min(inf_ms), 0.0 if inflate_ok else 1.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_nogather, te * 1e3, min(inf_ms), 0.0 if inflate_ok else 1.0, n / fd_gbs / 1e6 if fd_gbs else 1e12],
+                     dtype=torch.float64, device=dev)
     tot = torch.tensor([float(n), float(out_len)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_nogather, te_ms, inf_best_ms, inf_bad = t.tolist()
+    ms, ms_nogather, te_ms, inf_best_ms, inf_bad, fd_ms = t.tolist()
     n_total, out_total = tot.tolist()
 
-    if rank == 0:
-        import zlib
+    peak, peak_src = measured_peak()
+    del d_outs, d_out, gather_bufs
+    torch.cuda.empty_cache()
+    others = None
+    if not args.no_other_workloads:
+        others = other_workloads(D, comp, dev, rank, world, stream, dist, peak)
 
-        # correctness of what was timed (outside the timed region): the rank-0 stream inflates to the input
-        stream_bytes = h_out[:z_len].numpy().tobytes()
-        ok = zlib.decompress(stream_bytes) == host[hist:].tobytes() if world == 1 else None
-        peak, peak_src = measured_peak()
+    if rank == 0:
         km = sum(k_match_ms) / len(k_match_ms)          # ms of k_match per step (one launch per 256 MiB chunk)
         algo_bytes = n + out_len                        # 1 B read + 1/ratio B written per input byte
         achieved = algo_bytes / (km * 1e-3) / 1e9
@@ -362,15 +586,20 @@ def run_gpu(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "256 MiB order-2 Markov text per GPU (BASELINE configs[1], seed 2, 32 MiB stripes)",
                        "window": WINDOW, "segment_bytes": 32768, "chain_limit": 0, "block_mode": "cheapest (all dynamic)",
-                       "l2": "inputs larger than L2 (256 MiB per step)", "sharding": f"contiguous, {world} rank(s)"},
+                       "l2": "inputs larger than L2 (256 MiB per step)", "sharding": f"contiguous, {world} rank(s)",
+                       "cpu_binding": binding},
             "compression_ratio": n_total / out_total,
-            "roundtrip_ok": ok,
+            "roundtrip_ok": roundtrip_ok,
+            "roundtrip_check": roundtrip_what,
             "clocks": clocks,
             "e2e": {"value": n_total * e2e_steps / (te_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n),
-                    "d2h_bytes_per_step": int(z_len), "steps": e2e_steps,
-                    "call": "dfl_b200_compress_host (behind deflate_compress): pinned host in/out"},
+                    "d2h_bytes_per_step": int(z_len), "steps": e2e_steps, "roundtrip_ok": e2e_ok,
+                    "call": "dfl_b200_compress_host: pinned host in/out, H2D + D2H inside"},
+            "e2e_fd": {"value": n_total / (fd_ms * 1e-3) / 1e9 if fd_ms < 1e11 else None, "unit": "GB/s", "roundtrip_ok": fd_ok,
+                       "call": "deflate_compress(memfd_in, memfd_out, -1, 32768, 0): read(2)/pread(2) + H2D + kernels + D2H + "
+                               "write(2) inside, best of 3" + ("" if not fd_rc else f" (error {fd_rc})")},
             "gpu_launches": int(launches),
-            "kernel_ms_per_step": {k: v for k, v in comp.kernel_ms().items()},
+            "kernel_ms_per_step": {k: v for k, v in kernel_ms.items()},
             "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": km},
@@ -378,6 +607,8 @@ def run_gpu(args) -> None:
         line["inflate"] = {"value": n_total / (inf_best_ms * 1e-3) / 1e9, "unit": "GB/s of output (device-timed, k_inflate + "
                            "k_inf_resolve + k_inf_finish, best of 3)", "ms": inf_best_ms, "pointer_jumping_rounds": inflate_rounds,
                            "roundtrip_ok": inf_bad == 0.0}
+        if others is not None:
+            line["other_workloads"] = others
         if world > 1:
             line["compress_only_value"] = n_total * args.steps / (ms_nogather * 1e-3) / 1e9
         # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's single-threaded compressor ----
@@ -412,6 +643,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the passes over configs 3, 4 and 5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -68,6 +68,7 @@ struct dfl_ctx {
     int parse_mode; /* 0 = by segment count, 1 = k_parse_warp, 2 = k_parse */
     int match_mode; /* 0 = k_match_run where the geometry allows, 1 = always k_match */
     int num_sms;
+    size_t scratch_persist; /* bytes of the scratch asked to persist in L2 (0: not supported) */
     /* segment index of the last compress call (byte offset of every segment in the body, + the end) and inflate state */
     unsigned long long *seg_index;
     size_t seg_index_cap, seg_index_n;
@@ -243,6 +244,15 @@ extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
         return DFL_E_CUDA;
     }
     ctx->num_sms = prop.multiProcessorCount < SCRATCH_SLOTS ? prop.multiProcessorCount : SCRATCH_SLOTS;
+    /* k_match's scratch (radix park, the window block's offsets: 128 KB per resident CTA, reused segment after segment)
+     * is asked to stay in L2: without it the input streaming through evicts it and every segment writes it back to HBM */
+    ctx->scratch_persist = (size_t)ctx->num_sms * SCRATCH_STRIDE * sizeof(uint16_t);
+    if ((size_t)prop.persistingL2CacheMaxSize < ctx->scratch_persist) ctx->scratch_persist = (size_t)prop.persistingL2CacheMaxSize;
+    if ((size_t)prop.accessPolicyMaxWindowSize < ctx->scratch_persist) ctx->scratch_persist = (size_t)prop.accessPolicyMaxWindowSize;
+    if (ctx->scratch_persist && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->scratch_persist) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->scratch_persist = 0;
+    }
     *out = ctx;
     return DFL_OK;
 }
@@ -373,6 +383,16 @@ static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist
                         size_t nseg, uint8_t *d_out, size_t out_cap, cudaStream_t st)
 {
     const dfl_params prm = ctx->prm;
+    if (ctx->scratch_persist) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = ctx->scratch;
+        av.accessPolicyWindow.num_bytes = ctx->scratch_persist;
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
     /* the default geometry (the window of a segment is the segment before it): runs of consecutive segments per
      * CTA, the window's index inherited (k_match_run); anything else: one CTA per segment (k_match) */
     if (!ctx->match_mode && prm.seg_bytes == DFL_MAX_SEG && prm.window == DFL_MAX_WINDOW && prm.use_dict && !prm.chain_limit) {

@@ -29,7 +29,7 @@ extern "C" uint32_t dfl_b200_adler32_combine(uint32_t a1, uint32_t a2, uint64_t 
 /* ------------------------------------------------------------------------- */
 
 #ifndef FD_PIECE_BYTES
-#define FD_PIECE_BYTES (64u << 20) /* one pipeline piece */
+#define FD_PIECE_BYTES (32u << 20) /* one pipeline piece; the first ones are smaller (8, 16 MiB) so that the pipeline fills fast */
 #endif
 #define FD_IN_SLOTS 3  /* pinned input pieces: one being read, one being copied, one being compressed */
 #define FD_OUT_SLOTS 2 /* pinned output pieces: one being filled by the GPU, one being written */
@@ -114,6 +114,44 @@ extern "C" int dfl_b200_set_fd_piece(dfl_ctx *ctx, size_t bytes)
     return DFL_OK;
 }
 
+/* bytes of piece i: a ramp (quarter, half) up to the full piece, in whole segments */
+static size_t fd_piece_len(size_t piece, size_t seg, long i)
+{
+    size_t p = i == 0 ? piece / 4 : i == 1 ? piece / 2 : piece;
+    p = p / seg * seg;
+    if (p < DFL_MAX_WINDOW) p = (DFL_MAX_WINDOW + seg - 1) / seg * seg; /* a piece holds the next one's window */
+    return p < piece ? p : piece;
+}
+
+/* write(2) of one output piece; a regular file takes it from several threads with pwrite(2) */
+static int fd_write_piece(int fd, bool regular, unsigned long long file_off, const uint8_t *p, size_t n)
+{
+    if (!regular || n < (8u << 20)) {
+        if (regular && lseek(fd, (off_t)file_off, SEEK_SET) < 0) return -1;
+        return fd_write_all(fd, p, n);
+    }
+    const int nt = FD_IO_THREADS;
+    const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+    bool bad = false;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        th.emplace_back([=, &bad] {
+            size_t q = lo;
+            while (q < hi) {
+                const ssize_t w = pwrite(fd, p + q, hi - q, (off_t)(file_off + q));
+                if (w < 0 && errno == EINTR) continue;
+                if (w <= 0) { bad = true; return; }
+                q += (size_t)w;
+            }
+        });
+    }
+    for (auto &t : th) t.join();
+    if (bad) return -1;
+    return lseek(fd, (off_t)(file_off + n), SEEK_SET) < 0 ? -1 : 0; /* as write(2) would have left it */
+}
+
 namespace {
 struct FdPipe {
     std::mutex mu;
@@ -174,20 +212,29 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
                 if (P.out_err) return;
             }
             const int s = (int)(i % FD_IN_SLOTS);
-            const long long got = fd_read_piece(fd_in, regular, off, ctx->fd_h_in[s], piece);
+            const size_t want = fd_piece_len(piece, (size_t)prm.seg_bytes, i);
+            const long long got = fd_read_piece(fd_in, regular, off, ctx->fd_h_in[s], want);
             std::lock_guard<std::mutex> lk(P.mu);
             if (got < 0) { P.in_err = true; P.in_eof = true; P.cv.notify_all(); return; }
             off += (unsigned long long)got;
             P.in_len[s] = (size_t)got;
             P.in_ready = i + 1;
-            if ((size_t)got < piece) P.in_eof = true;
+            if ((size_t)got < want) P.in_eof = true;
             P.cv.notify_all();
-            if ((size_t)got < piece) return;
+            if ((size_t)got < want) return;
         }
     });
+    struct stat st_out;
+    const bool regular_out = fd_out >= 0 && fstat(fd_out, &st_out) == 0 && S_ISREG(st_out.st_mode);
+    unsigned long long out_off = 0;
+    if (regular_out) {
+        const off_t cur = lseek(fd_out, 0, SEEK_CUR);
+        out_off = cur > 0 ? (unsigned long long)cur : 0;
+    }
     std::thread writer([&] {
         static const uint8_t hdr[2] = {0x78, 0x9C}; /* CM = 8, CINFO = 7, FCHECK: what src/deflate_decompress.c:352-360 checks */
         bool bad = fd_out >= 0 && fd_write_all(fd_out, hdr, 2) != 0;
+        unsigned long long woff = out_off + 2;
         for (long j = 0;; j++) {
             size_t len;
             {
@@ -197,7 +244,8 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
                 if (P.out_ready <= j) return;
                 len = P.out_len[j % FD_OUT_SLOTS];
             }
-            if (!bad && fd_out >= 0 && fd_write_all(fd_out, ctx->fd_h_out[j % FD_OUT_SLOTS], len) != 0) bad = true;
+            if (!bad && fd_out >= 0 && fd_write_piece(fd_out, regular_out, woff, ctx->fd_h_out[j % FD_OUT_SLOTS], len) != 0) bad = true;
+            woff += len;
             std::lock_guard<std::mutex> lk(P.mu);
             P.out_done = j + 1;
             if (bad) P.out_err = true;
@@ -237,7 +285,7 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
         const int ds = (int)(i & 1);
         const size_t len = len_cur, hist = i == 0 ? 0 : (total_in < W ? (size_t)total_in : W);
         /* a piece that fills its slot may or may not be the last one: the next read tells (it overlapped piece i - 1) */
-        bool last = len < piece;
+        bool last = len < fd_piece_len(piece, (size_t)prm.seg_bytes, i);
         if (!last) {
             if (!wait_piece(i + 1, &len_next)) { rc = DFL_E_INVAL; break; }
             last = len_next == 0;

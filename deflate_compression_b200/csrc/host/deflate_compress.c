@@ -8,6 +8,7 @@
 #define _GNU_SOURCE
 #include <errno.h>
 #include <limits.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -36,6 +37,28 @@ static int map_err(int rc)
     }
 }
 
+/* A context is expensive to make (device workspace, pinned pipeline pieces), deflate_compress() makes one per call
+ * (src/deflate_compress.c:364-366 does): the last one is parked here and taken again by the next call with the same
+ * window instead of being destroyed; it is released when the process exits. */
+static pthread_mutex_t parked_mu = PTHREAD_MUTEX_INITIALIZER;
+static dfl_ctx *parked_ctx;
+static int parked_window, parked_device, parked_atexit;
+
+/* The reference's entry points have no device argument: DFL_B200_DEVICE (default 0) picks the GPU. */
+static int env_device(void)
+{
+    const char *e = getenv("DFL_B200_DEVICE");
+    return e && *e ? atoi(e) : 0;
+}
+
+static void parked_release(void)
+{
+    pthread_mutex_lock(&parked_mu);
+    dfl_b200_destroy(parked_ctx);
+    parked_ctx = NULL;
+    pthread_mutex_unlock(&parked_mu);
+}
+
 deflate_compr_t *spawn_deflate_compr_t(void)
 {
     return (deflate_compr_t *)calloc(1, sizeof(deflate_compr_t));
@@ -54,15 +77,31 @@ void deflate_compr_init(deflate_compr_t *com, int fd_in, int fd_out, int fd_stat
     com->ctx = NULL;
     com->err = 0;
     if (sw < 1 || sw > DFL_MAX_WINDOW) { com->err = -E_RANGE; return; }
+    pthread_mutex_lock(&parked_mu);
+    if (parked_ctx && parked_window == (int)sw && parked_device == env_device()) {
+        com->ctx = parked_ctx;
+        parked_ctx = NULL;
+    }
+    pthread_mutex_unlock(&parked_mu);
+    if (com->ctx) return;
     dfl_b200_default_params(&prm);
     prm.window = sw;
-    com->err = map_err(dfl_b200_create(&com->ctx, 0, &prm));
+    com->err = map_err(dfl_b200_create(&com->ctx, env_device(), &prm));
 }
 
 void deflate_compr_deinit(deflate_compr_t *com)
 {
-    if (!com) return;
-    dfl_b200_destroy(com->ctx);
+    dfl_ctx *old = NULL;
+    if (!com || !com->ctx) return;
+    dfl_b200_keep_tokens(com->ctx, 0);
+    pthread_mutex_lock(&parked_mu);
+    old = parked_ctx;
+    parked_ctx = com->ctx;
+    parked_window = (int)com->sliding_window;
+    parked_device = env_device();
+    if (!parked_atexit) { parked_atexit = 1; atexit(parked_release); }
+    pthread_mutex_unlock(&parked_mu);
+    dfl_b200_destroy(old);
     com->ctx = NULL;
 }
 

@@ -458,7 +458,9 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
     const long long t2 = clock64();
 
     /* ---- speculative chunk parsers (k_search.cuh) ---- */
-    if (warp < SEARCH_WARPS)
+    if (!HAS_K && sb == 0) /* hardly any repetition: every position's match, flat over the list */
+        search_flat<false>(S, soff, hist, seglen, prm.window, NI, 0, tokcand + (size_t)blockIdx.x * prm.seg_bytes, nullptr, tid);
+    else if (warp < SEARCH_WARPS)
         search_segment<HAS_K, false>(S, soff, hist, seglen, prm.window, HAS_K ? prm.chain_limit : 0, sb,
                                      tokcand + (size_t)blockIdx.x * prm.seg_bytes, nullptr, state, lane, warp, t2);
     __syncthreads();

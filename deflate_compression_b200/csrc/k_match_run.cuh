@@ -107,6 +107,19 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
             const int ni_old_fresh = (lim < B ? lim : B) - P0 > 0 ? (lim < B ? lim : B) - P0 : 0;
             const int ni_seg = (lim < B + seglen ? lim : B + seglen) - B > 0 ? (lim < B + seglen ? lim : B + seglen) - B : 0;
 
+#ifdef RUN_SINGLE /* experiment: k_match's own algorithm (one list over window + segment) inside this kernel's loop */
+            {
+                const int NI = lim - P0 > 0 ? lim - P0 : 0;
+                if (!build_index<true>(S, soff, P0, 0, NI, gbuf, tid, lane, warp, state, sb)) build_index<false>(S, soff, P0, 0, NI, gbuf, tid, lane, warp, state, sb);
+                const long long t2 = clock64();
+                if (tid == 0) { atomicAdd(&state->t_phase[0], (unsigned long long)(t1 - t0)); atomicAdd(&state->t_phase[1], (unsigned long long)(t2 - t1)); }
+                if (warp < SEARCH_WARPS) search_segment<false, false>(S, soff, B, seglen, B, 0, sb, tokcand + (size_t)sl * B, oo, state, lane, warp, t2);
+                __syncthreads();
+                if (tid == 0) atomicAdd(&state->t_phase[2], (unsigned long long)(clock64() - t2));
+                __syncthreads();
+                continue;
+            }
+#endif
             if (first) {
                 /* bucket width for the run (k_match decides per segment): plain trigram buckets for data with hardly
                  * any repetition, 4-byte buckets otherwise; sum of squared trigram-bucket counts of a 1-in-8 sample */
@@ -148,6 +161,7 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
             /* the window block's bucket offsets go to global scratch, two per word (S.off still holds them) */
             for (int b = tid; b <= HASH_SIZE; b += MATCH_THREADS) __stcg(oo + b, (uint32_t)S.off[b] | ((uint32_t)S.off[b + 1] << 16));
             if (tid == 0 && sb == 0) atomicAdd(&state->t_phase[20], 1ull); /* segments indexed by plain trigram buckets */
+            __threadfence(); /* gpu scope: also drops this SM's L1 lines of the previous segment's offsets (the search reads them through L1) */
             __syncthreads();
 
             /* ---- the segment block's list ---- */
@@ -163,7 +177,9 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
             }
 
             /* ---- speculative chunk parsers (k_search.cuh) ---- */
-            if (warp < SEARCH_WARPS)
+            if (sb == 0) /* hardly any repetition: every position's match, flat over the list */
+                search_flat<true>(S, soff, B, seglen, B, ni_seg, 0, tokcand + (size_t)sl * B, oo, tid);
+            else if (warp < SEARCH_WARPS)
                 search_segment<false, true>(S, soff, B, seglen, B, 0, sb, tokcand + (size_t)sl * B, oo, state, lane, warp, t2);
             __syncthreads();
 #ifdef DFL_SEARCH_STATS

@@ -2,6 +2,9 @@
  * shared by k_match and k_match_run). */
 #pragma once
 
+#ifndef OO_LOAD
+#define OO_LOAD __ldca /* the window block's offsets are read through L1 (k_match_run invalidates it after writing them) */
+#endif
 #define RUN_BLK 32768    /* k_match_run: frame position of the segment start = slot of the old block's list */
 
 /*
@@ -66,7 +69,7 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 pw1 = ld4s(dbase + p + 4);                                              \
                 foff = 0; fmask = fmask0; fword = pw0 & fmask0;                         \
                 const uint32_t b_ = hash4(pw0, ngrp, sb);                               \
-                if (TWO) ow = __ldcg(oo + b_);                                                                    \
+                if (TWO) ow = OO_LOAD(oo + b_);                                                                    \
                 k_lo = (int)lds_u16(obase + 2 * b_);                                    \
                 k = k_lo;                                                               \
                 k_hi = (int)lds_u16(obase + 2 * b_ + 2);                                \
@@ -299,7 +302,7 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 const uint32_t hw = __shfl_sync(FULL, pw0, L) & 0xFFFFFFu;
                 const uint32_t g_ = hash4(hw, ngrp, sb); /* fourth byte 0 -> first bucket of the group */
                 uint32_t og0 = 0, og1 = 0;
-                if (TWO) { og0 = __ldcg(oo + g_); og1 = __ldcg(oo + g_ + (1 << DFL_SUB_BITS) - 1); } /* in flight during the first sweep */
+                if (TWO) { og0 = OO_LOAD(oo + g_); og1 = OO_LOAD(oo + g_ + (1 << DFL_SUB_BITS) - 1); } /* in flight during the first sweep */
                 int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
                 uint32_t gl = lbase;
                 uint32_t loc = 0;
@@ -381,4 +384,76 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
     (void)state; (void)t2;
 #endif
 #undef INIT_HEAD
+}
+
+/*
+ * The same search for segments indexed by plain trigram buckets (sb == 0: data with hardly any repetition --
+ * ciphertext, compressed payloads; a bucket holds a handful of positions): M(p) for EVERY position of the segment, a
+ * thread per list slot, no parse heads, no chains, no claims.  Slot k holds position p; its candidates are the slots
+ * before it in its bucket (the segment block's list, nearest first), then, TWO only, the window block's bucket from its
+ * newest entry down to the window's edge.  Longest wins, the nearest on ties (strict '>', src/deflate_compress.c:258);
+ * k_parse then follows the chain of tokens from position 0.  Positions the index does not hold (the last ones of the
+ * input, which have no whole trigram) are literals.
+ */
+template <bool TWO>
+__device__ __forceinline__ void search_flat(MatchSmem &S, const uint32_t soff, const int hist, const int seglen, const int W,
+                                            const int ni_seg, const int lofs_seg, uint32_t *__restrict__ out,
+                                            const uint32_t *__restrict__ oo, const int tid)
+{
+    const uint32_t ngrp = HASH_SIZE;
+    uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
+    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
+    uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
+    asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
+    /* !TWO: the list holds the window's positions too; only the segment's get a token */
+    for (int k = tid; k < ni_seg; k += MATCH_THREADS) {
+        const int p = (int)lds_u16(lbase + 2 * (lofs_seg + k));
+        const int i = p - hist;
+        if (i < 0) continue;
+        const int maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;
+        uint32_t tok = lds_u8(dbase + p);
+        if (maxlen >= DFL_MIN_MATCH) {
+            const uint32_t pw0 = ld4s(dbase + p);
+            const uint32_t b_ = hash4(pw0, ngrp, 0);
+            int best_len = 2, best_q = 0;
+            int kk = lofs_seg + k - 1, lo = lofs_seg + (int)lds_u16(obase + 2 * b_);
+#pragma unroll 1
+            for (int part = 0; part < (TWO ? 2 : 1); part++) {
+                for (; kk >= lo; kk--) {
+                    const int q = (int)lds_u16(lbase + 2 * kk);
+                    if (p - q > W) { part = 2; break; } /* everything older is outside the window */
+                    const uint32_t x0 = ld4s(dbase + q) ^ pw0;
+                    if (x0 & 0xFFFFFFu) continue; /* another trigram of the bucket */
+                    int len = 3;
+                    if (!(x0 >> 24)) {
+                        len = 4;
+                        while (len < maxlen) {
+                            const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
+                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                            len += 4;
+                        }
+                    }
+                    if (len > maxlen) len = maxlen;
+                    if (len > best_len) { best_len = len; best_q = q; }
+                }
+                if (TWO && part == 0 && best_len < maxlen) {
+                    const uint32_t ow = OO_LOAD(oo + b_);
+                    lo = RUN_BLK + (int)(ow & 0xFFFF);
+                    kk = RUN_BLK + (int)(ow >> 16) - 1;
+                } else {
+                    break;
+                }
+            }
+            if (best_len >= DFL_MIN_MATCH) tok = ((uint32_t)(p - best_q) << 16) | (uint32_t)best_len;
+        }
+        out[i] = tok;
+    }
+    /* positions without a whole trigram in the data: the index does not hold them */
+    for (int i = tid; i < seglen; i += MATCH_THREADS) {
+        const int p = hist + i;
+        bool indexed;
+        if (TWO) indexed = i < ni_seg;
+        else indexed = p < ni_seg; /* !TWO: ni_seg counts all positions of [window | segment] */
+        if (!indexed) out[i] = lds_u8(dbase + p);
+    }
 }
