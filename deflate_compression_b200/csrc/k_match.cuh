@@ -28,7 +28,11 @@
 #define SORT_WARPS 32    /* every warp sorts one stripe */
 #define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
 #define SCRATCH_SLOTS 256
-#define SCRATCH_STRIDE NPOS_MAX /* u16 units per slot: k_match parks 64 Ki positions; k_match_run 32 Ki + the window block's bucket offsets */
+/* u16 units of global scratch per slot (a slot belongs to one resident CTA): the radix park (64 Ki positions for
+ * k_match; k_match_run uses the first 32 Ki) and k_match_run's two saved blocks (sorted positions, their buckets,
+ * bucket offsets), which take turns as "the segment's block" and "the window's block" */
+#define SAVED_BLK (32768 + 32768 + 16384)
+#define SCRATCH_STRIDE (NPOS_MAX + 2 * SAVED_BLK)
 
 struct MatchSmem {
     uint32_t data[(NPOS_MAX + 64) / 4]; /* [window | segment] bytes, 16 B of slack either side */
@@ -220,10 +224,11 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int pos0,
 }
 
 /* Sort the NI positions [pos0, pos0 + NI) by (bucket, position) into S.list[lofs, lofs + NI) and fill the
- * bucket offsets (relative to lofs).  Returns (to every thread) whether the order verified. */
+ * bucket offsets (relative to lofs); bkt_out (global, optional) receives the bucket of every slot.  Returns (to
+ * every thread) whether the order verified. */
 template <bool FAST>
 __device__ __noinline__ bool build_index(MatchSmem &S, uint32_t soff, int pos0, int lofs, int NI, uint16_t *gbuf, int tid, int lane,
-                                            int warp, DevState *state, int sb)
+                                            int warp, DevState *state, int sb, uint16_t *bkt_out = nullptr)
 {
     const uint32_t ngrp = HASH_SIZE >> sb;
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
@@ -264,6 +269,8 @@ __device__ __noinline__ bool build_index(MatchSmem &S, uint32_t soff, int pos0, 
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)hash4(ld4s(dbase + q[j]), ngrp, sb) : HASH_SIZE;
+        /* k_match_run keeps every slot's bucket beside the list it saves for the next segment's merge */
+        if (bkt_out && kk0 < NI) __stcg(reinterpret_cast<uint2 *>(bkt_out + kk0), make_uint2((uint32_t)b[0] | ((uint32_t)b[1] << 16), (uint32_t)b[2] | ((uint32_t)b[3] << 16)));
         int pq = __shfl_up_sync(FULL, q[3], 1), pb_ = __shfl_up_sync(FULL, b[3], 1);
         if (lane == 0) {
             pq = kk0 > 0 && kk0 <= NI ? (int)lds_u16(lbase + 2 * (kk0 - 1)) : -1;
@@ -459,10 +466,10 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
 
     /* ---- speculative chunk parsers (k_search.cuh) ---- */
     if (!HAS_K && sb == 0) /* hardly any repetition: every position's match, flat over the list */
-        search_flat<false>(S, soff, hist, seglen, prm.window, NI, 0, tokcand + (size_t)blockIdx.x * prm.seg_bytes, nullptr, tid);
+        search_flat(S, soff, hist, seglen, prm.window, NI, NI, tokcand + (size_t)blockIdx.x * prm.seg_bytes, tid);
     else if (warp < SEARCH_WARPS)
-        search_segment<HAS_K, false>(S, soff, hist, seglen, prm.window, HAS_K ? prm.chain_limit : 0, sb,
-                                     tokcand + (size_t)blockIdx.x * prm.seg_bytes, nullptr, state, lane, warp, t2);
+        search_segment<HAS_K>(S, soff, hist, seglen, prm.window, HAS_K ? prm.chain_limit : 0, sb,
+                              tokcand + (size_t)blockIdx.x * prm.seg_bytes, state, lane, warp, t2);
     __syncthreads();
 #ifdef DFL_SEARCH_STATS
     if (warp == 0 && warp < SEARCH_WARPS) {

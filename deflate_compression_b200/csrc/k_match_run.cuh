@@ -5,6 +5,7 @@
 #ifndef RUN_SEGS
 #define RUN_SEGS 8 /* consecutive segments one CTA takes in a row (the first one sorts its window itself) */
 #endif
+#define RUN_BLK 32768   /* block size = frame position of the segment */
 #define RUN_LOOKAHEAD 4 /* bytes past the segment staged with it: its last positions are hashed over their real 4 bytes */
 
 /*
@@ -13,13 +14,17 @@
  * dictionary priming on, no chain limit -- where the window of a segment IS the segment before it.
  *
  * k_match sorts all 65536 positions of [window | segment] for every segment, so every byte is sorted twice
- * (once as segment, once as the next segment's window).  Here a CTA takes RUN_SEGS consecutive segments.
- * All positions of the window precede all positions of the segment, so a bucket of the combined index is
- * exactly [window block's entries | segment block's entries]: the two blocks keep separate lists, only the
- * segment block is sorted, and the list it leaves behind becomes the window block's list of the next segment
- * (positions rebased by 32768; bucket offsets packed two per word into global scratch, which stays in L2).
- * search_segment<_, TWO = true> walks a bucket through the segment block's list first and then through the
- * window block's.  Only the first segment of a run has to sort its window itself.
+ * (once as segment, once as the next segment's window).  Here a CTA takes RUN_SEGS consecutive segments and
+ * sorts only the segment's own 32768 positions.  All positions of the window precede all positions of the
+ * segment, so a bucket of the combined index is exactly [window block's entries | segment block's entries]:
+ * the combined list is the bucket-wise concatenation of the two blocks' sorted lists, and its offsets are the
+ * sums of theirs.  Every sorted block is saved to global scratch (positions, the bucket of every slot, bucket
+ * offsets; 160 KB per block, two slots per CTA, L2 resident) and is merged twice: now as the segment's block,
+ * and by the next segment as its window's block.  The merge is two linear sweeps with one shared-memory lookup
+ * per entry (the other block's offset of that bucket).  The search is k_match's (search_segment), over a list laid
+ * out exactly as k_match's.  Only the first segment of a run has to sort its window itself.
+ * (Keeping the two lists apart and handing a bucket walk over from one to the other was measured first: the same
+ * walk steps, but 24 % more time per step of the search loop -- more than the saved sorting.)
  *
  * Frame: position P of the shared-memory frame is input byte seg_lo - 32768 + P; the window block is
  * [32768 - hist, 32768), the segment block [32768, 32768 + seglen).  The RUN_LOOKAHEAD bytes after the
@@ -33,20 +38,35 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MatchSmem &S = *reinterpret_cast<MatchSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int B = RUN_BLK; /* 32768: block size, frame position of the segment, list slot of the window block */
+    constexpr int B = RUN_BLK; /* 32768: block size, frame position of the segment */
     const uint32_t soff = 16 + (uint32_t)((uintptr_t)d_in & 15); /* frame byte P lives at smem byte soff + P (seg_lo is a multiple of 16) */
     uint8_t *sd = reinterpret_cast<uint8_t *>(S.data);
-    uint16_t *gbuf = scratch + (size_t)blockIdx.x * SCRATCH_STRIDE;       /* radix park: 32 Ki positions */
-    uint32_t *oo = reinterpret_cast<uint32_t *>(gbuf + B);                 /* window block's offsets: oo[b] = off[b] | off[b + 1] << 16 */
+    uint16_t *gbuf = scratch + (size_t)blockIdx.x * SCRATCH_STRIDE; /* radix park: 32 Ki positions */
+    uint16_t *saved[2] = {gbuf + NPOS_MAX, gbuf + NPOS_MAX + SAVED_BLK}; /* a saved block: pos[32768] | bucket[32768] | off[HASH_SIZE + 2] */
+    uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list), obase = (uint32_t)__cvta_generic_to_shared(S.off);
     const int nruns = (ns + run_segs - 1) / run_segs;
     uint32_t bar_phase = 0;
     if (tid == 0) mbar_init(&S.bar, 1);
     __syncthreads();
 
+    /* sort the ni positions from pos0 on, save the block (sorted positions, buckets, offsets) to slot w */
+    auto sort_and_save = [&](int pos0, int ni, int sb, int w) {
+        if (!build_index<true>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B)) {
+            /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
+            if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
+            build_index<false>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B);
+        }
+        for (int k8 = tid * 8; k8 < ni; k8 += MATCH_THREADS * 8)
+            __stcg(reinterpret_cast<uint4 *>(saved[w] + k8), *reinterpret_cast<const uint4 *>(&S.list[k8]));
+        for (int b2 = tid; b2 < (HASH_SIZE + 2) / 2; b2 += MATCH_THREADS)
+            __stcg(reinterpret_cast<uint32_t *>(saved[w] + 2 * B) + b2, reinterpret_cast<const uint32_t *>(S.off)[b2]);
+        __syncthreads();
+    };
+
     for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
         const int sA = run * run_segs, sB = sA + run_segs < ns ? sA + run_segs : ns; /* segments of this launch */
         int sb = DFL_SUB_BITS;
-        int ni_new = 0; /* entries of the segment block's list (of the previous segment when the loop body starts) */
+        int ni_win = 0, w_win = 0; /* the window's block: entries, slot it is saved in */
         for (int sl = sA; sl < sB; sl++) {
             const long long t0 = clock64();
             const bool first = sl == sA;
@@ -58,7 +78,6 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
             const int la = n - seg_hi < RUN_LOOKAHEAD ? (int)(n - seg_hi) : RUN_LOOKAHEAD;
             const int P0 = B - hist, Pend = B + seglen + la; /* staged frame positions */
             const uint8_t *g0 = d_in + (seg_lo - hist);      /* = frame position P0 */
-
             /* ---- stage [window | segment | lookahead] (TMA bulk copy for the aligned interior) ---- */
             {
                 const int npos = Pend - P0;
@@ -104,33 +123,20 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
 
             /* positions with a whole trigram inside the data: P + 3 <= Pend */
             const int lim = Pend - 2;
-            const int ni_old_fresh = (lim < B ? lim : B) - P0 > 0 ? (lim < B ? lim : B) - P0 : 0;
+            const int ni_win_fresh = (lim < B ? lim : B) - P0 > 0 ? (lim < B ? lim : B) - P0 : 0;
             const int ni_seg = (lim < B + seglen ? lim : B + seglen) - B > 0 ? (lim < B + seglen ? lim : B + seglen) - B : 0;
 
-#ifdef RUN_SINGLE /* experiment: k_match's own algorithm (one list over window + segment) inside this kernel's loop */
-            {
-                const int NI = lim - P0 > 0 ? lim - P0 : 0;
-                if (!build_index<true>(S, soff, P0, 0, NI, gbuf, tid, lane, warp, state, sb)) build_index<false>(S, soff, P0, 0, NI, gbuf, tid, lane, warp, state, sb);
-                const long long t2 = clock64();
-                if (tid == 0) { atomicAdd(&state->t_phase[0], (unsigned long long)(t1 - t0)); atomicAdd(&state->t_phase[1], (unsigned long long)(t2 - t1)); }
-                if (warp < SEARCH_WARPS) search_segment<false, false>(S, soff, B, seglen, B, 0, sb, tokcand + (size_t)sl * B, oo, state, lane, warp, t2);
-                __syncthreads();
-                if (tid == 0) atomicAdd(&state->t_phase[2], (unsigned long long)(clock64() - t2));
-                __syncthreads();
-                continue;
-            }
-#endif
             if (first) {
                 /* bucket width for the run (k_match decides per segment): plain trigram buckets for data with hardly
                  * any repetition, 4-byte buckets otherwise; sum of squared trigram-bucket counts of a 1-in-8 sample */
                 uint32_t *off32 = reinterpret_cast<uint32_t *>(S.off);
-                const uint32_t obase_ = (uint32_t)__cvta_generic_to_shared(S.off), dbase_ = (uint32_t)__cvta_generic_to_shared(S.data) + soff + P0;
+                const uint32_t dbase_ = (uint32_t)__cvta_generic_to_shared(S.data) + soff + P0;
                 const int NI = lim - P0 > 0 ? lim - P0 : 0;
                 for (int i2 = tid; i2 < (HASH_SIZE + 2) / 2; i2 += MATCH_THREADS) off32[i2] = 0;
                 __syncthreads();
                 for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
                     const uint32_t b = DFL_HASH3(ld4s(dbase_ + k8));
-                    reds_add(obase_ + 4 * (b >> 1), 1u << ((b & 1) * 16));
+                    reds_add(obase + 4 * (b >> 1), 1u << ((b & 1) * 16));
                 }
                 __syncthreads();
                 uint32_t sq = 0;
@@ -144,44 +150,79 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
                 sq = __reduce_add_sync(FULL, S.scan_w[lane]);
                 __syncthreads();
                 sb = sq <= SPLIT_MIN_SQ * ((uint32_t)(NI + 7) / 8) ? 0 : DFL_SUB_BITS;
-                /* the window block's list, sorted here for the first segment of the run only */
-                if (!build_index<true>(S, soff, P0, B, ni_old_fresh, gbuf, tid, lane, warp, state, sb)) {
-                    if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-                    build_index<false>(S, soff, P0, B, ni_old_fresh, gbuf, tid, lane, warp, state, sb);
-                }
-            } else {
-                /* the previous segment's block has become the window: its list moves to the window block's slots,
-                 * rebased by one block (its entries are 32768 + position) */
-                for (int k8 = tid * 8; k8 < ni_new; k8 += MATCH_THREADS * 8) {
-                    uint4 v = *reinterpret_cast<const uint4 *>(&S.list[k8]);
-                    v.x &= 0x7FFF7FFFu; v.y &= 0x7FFF7FFFu; v.z &= 0x7FFF7FFFu; v.w &= 0x7FFF7FFFu;
-                    *reinterpret_cast<uint4 *>(&S.list[B + k8]) = v;
-                }
+                /* the window's block, sorted here for the first segment of the run only */
+                w_win = 0;
+                ni_win = ni_win_fresh;
+                sort_and_save(P0, ni_win, sb, w_win);
             }
-            /* the window block's bucket offsets go to global scratch, two per word (S.off still holds them) */
-            for (int b = tid; b <= HASH_SIZE; b += MATCH_THREADS) __stcg(oo + b, (uint32_t)S.off[b] | ((uint32_t)S.off[b + 1] << 16));
             if (tid == 0 && sb == 0) atomicAdd(&state->t_phase[20], 1ull); /* segments indexed by plain trigram buckets */
-            __threadfence(); /* gpu scope: also drops this SM's L1 lines of the previous segment's offsets (the search reads them through L1) */
-            __syncthreads();
 
-            /* ---- the segment block's list ---- */
-            if (!build_index<true>(S, soff, B, 0, ni_seg, gbuf, tid, lane, warp, state, sb)) {
-                if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-                build_index<false>(S, soff, B, 0, ni_seg, gbuf, tid, lane, warp, state, sb);
+            /* ---- the segment's block: sorted and saved (the next segment merges it again, as its window) ---- */
+            const int w_seg = w_win ^ 1;
+            sort_and_save(B, ni_seg, sb, w_seg); /* S.off = the segment block's offsets */
+
+            /* The combined list has 16-bit offsets: 65536 entries (a full window and a full segment) are one too many.
+             * The segment's last position is no candidate for any head of this segment (it is the largest one) and is
+             * left out of the combined list; it stays in the saved block, the next segment needs it.  It is the last
+             * entry of its bucket's part of the segment block's list. */
+            int k_drop = 0x7FFFFFFF, b_drop = 0x7FFFFFFF;
+            if (ni_win + ni_seg > 65535) {
+                b_drop = (int)hash4(ld4s((uint32_t)__cvta_generic_to_shared(S.data) + soff + B + ni_seg - 1), HASH_SIZE >> sb, sb);
+                k_drop = (int)lds_u16(obase + 2 * b_drop + 2) - 1;
             }
-            ni_new = ni_seg;
+            /* ---- merge: bucket b of the combined list = [window block's entries of b | segment block's entries of b] ---- */
+            {
+                const uint16_t *wp = saved[w_win], *wb = wp + B, *sp = saved[w_seg], *sbk = sp + B;
+                /* a window entry at slot k of its list, bucket b, lands at k + (segment block's offset of b), less the
+                 * position left out if that one's bucket comes before b */
+                for (int k4 = tid * 4; k4 < ni_win; k4 += MATCH_THREADS * 4) {
+                    const uint2 pp = __ldcg(reinterpret_cast<const uint2 *>(wp + k4)), bb = __ldcg(reinterpret_cast<const uint2 *>(wb + k4));
+                    const uint32_t pos[4] = {pp.x & 0xFFFF, pp.x >> 16, pp.y & 0xFFFF, pp.y >> 16};
+                    const uint32_t bk[4] = {bb.x & 0xFFFF, bb.x >> 16, bb.y & 0xFFFF, bb.y >> 16};
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (k4 + j < ni_win) /* (a block saved as the segment's holds 32768 + position) */
+                            sts_u16(lbase + 2 * (k4 + j + lds_u16(obase + 2 * bk[j]) - ((int)bk[j] > b_drop ? 1 : 0)), pos[j] & (B - 1));
+                }
+                __syncthreads();
+                /* S.off <- the window block's offsets; a segment entry at slot k, bucket b, lands at k + (window block's offset of b + 1) */
+                for (int b2 = tid; b2 < (HASH_SIZE + 2) / 2; b2 += MATCH_THREADS)
+                    reinterpret_cast<uint32_t *>(S.off)[b2] = __ldcg(reinterpret_cast<const uint32_t *>(wp + 2 * B) + b2);
+                __syncthreads();
+                for (int k4 = tid * 4; k4 < ni_seg; k4 += MATCH_THREADS * 4) {
+                    const uint2 pp = __ldcg(reinterpret_cast<const uint2 *>(sp + k4)), bb = __ldcg(reinterpret_cast<const uint2 *>(sbk + k4));
+                    const uint32_t pos[4] = {pp.x & 0xFFFF, pp.x >> 16, pp.y & 0xFFFF, pp.y >> 16};
+                    const uint32_t bk[4] = {bb.x & 0xFFFF, bb.x >> 16, bb.y & 0xFFFF, bb.y >> 16};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int kk = k4 + j;
+                        if (kk < ni_seg && kk != k_drop) sts_u16(lbase + 2 * (kk - (kk > k_drop ? 1 : 0) + lds_u16(obase + 2 * bk[j] + 2)), pos[j]);
+                    }
+                }
+                __syncthreads();
+                /* combined offsets: the sum of the two blocks' (entry HASH_SIZE + 1 = the total) */
+                for (int b2 = tid; b2 < (HASH_SIZE + 2) / 2; b2 += MATCH_THREADS) { /* two offsets per word; no sum exceeds 65535 */
+                    const uint32_t dec = (2 * b2 > b_drop ? 1u : 0u) | (2 * b2 + 1 > b_drop ? 0x10000u : 0u);
+                    reinterpret_cast<uint32_t *>(S.off)[b2] += __ldcg(reinterpret_cast<const uint32_t *>(sp + 2 * B) + b2) - dec;
+                }
+                __syncthreads();
+            }
+            const int ni_all = ni_win + ni_seg - (k_drop != 0x7FFFFFFF ? 1 : 0);
             const long long t2 = clock64();
             if (tid == 0) {
                 atomicAdd(&state->t_phase[0], (unsigned long long)(t1 - t0));
                 atomicAdd(&state->t_phase[1], (unsigned long long)(t2 - t1));
             }
 
-            /* ---- speculative chunk parsers (k_search.cuh) ---- */
-            if (sb == 0) /* hardly any repetition: every position's match, flat over the list */
-                search_flat<true>(S, soff, B, seglen, B, ni_seg, 0, tokcand + (size_t)sl * B, oo, tid);
-            else if (warp < SEARCH_WARPS)
-                search_segment<false, true>(S, soff, B, seglen, B, 0, sb, tokcand + (size_t)sl * B, oo, state, lane, warp, t2);
+            /* ---- the search (k_search.cuh), over a list laid out as k_match's ---- */
+            if (sb == 0) { /* hardly any repetition: every position's match, flat over the list */
+                search_flat(S, soff, B, seglen, B, ni_all, lim, tokcand + (size_t)sl * B, tid);
+                if (k_drop != 0x7FFFFFFF && tid == 0) tokcand[(size_t)sl * B + seglen - 1] = sd[soff + B + seglen - 1]; /* the position left out of the list */
+            } else if (warp < SEARCH_WARPS)
+                search_segment<false>(S, soff, B, seglen, B, 0, sb, tokcand + (size_t)sl * B, state, lane, warp, t2);
             __syncthreads();
+            ni_win = ni_seg;
+            w_win = w_seg;
 #ifdef DFL_SEARCH_STATS
             if (warp == 0 && warp < SEARCH_WARPS) {
                 const uint32_t e = lane < SEARCH_WARPS ? S.scan_w[lane] : 0u;

@@ -2,38 +2,27 @@
  * shared by k_match and k_match_run). */
 #pragma once
 
-#ifndef OO_LOAD
-#define OO_LOAD __ldca /* the window block's offsets are read through L1 (k_match_run invalidates it after writing them) */
-#endif
-#define RUN_BLK 32768    /* k_match_run: frame position of the segment start = slot of the old block's list */
-
 /*
  * process_loop's match search AND its greedy token decision (src/deflate_compress.c:243-288) for one
- * segment whose bytes and index are in shared memory.
+ * segment whose bytes and index are in shared memory: S.list holds every position of [window | segment]
+ * sorted by (bucket, position), S.off the bucket offsets; position `hist` of that frame is the segment's first byte.
  *
- * Index layout.  !TWO (k_match): S.list holds every position of [window | segment] sorted by (bucket,
- * position), S.off the bucket offsets.  TWO (k_match_run): the segment block's positions are S.list[0, 32768)
- * with offsets S.off, the window block's positions (inherited from the previous segment of the run) are
- * S.list[32768, 65536) with their offsets packed in global memory (oo[b] = start | end << 16); a bucket is
- * walked through the segment block first, then handed over to the window block.
- *
- * Parse.  The longest / nearest match M(p) = argmax_{q in [max(lo, p-window), p-1]} lcp(q, p) (ties ->
+ * The longest / nearest match M(p) = argmax_{q in [max(lo, p-window), p-1]} lcp(q, p) (ties ->
  * nearest, capped at min(258, seg_hi - p)) is a pure function of the bytes, because every position is
  * indexed and buckets are walked to the end.  Only parse heads need it.  The segment is cut into 32-byte
  * chunks; every lane takes a chunk, parses greedily from the chunk start as if it were a head (:265-288:
  * len >= 3 -> advance len, else literal, advance 1) and KEEPS GOING past the chunk end until it steps on a
  * position another lane has already claimed (shared bitmap, atomicOr) or leaves the segment.  By induction
- * from position 0 (claimed by chunk 0's lane) every head of the true greedy parse is claimed and evaluated.
+ * from position 0 (claimed by chunk 0's lane) every head of the true greedy parse is claimed and evaluated;
+ * speculative parses re-synchronise with the true one within a few tokens.  k_parse then follows the evaluated heads.
  */
-template <bool HAS_K, bool TWO>
+template <bool HAS_K>
 __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff, const int hist, const int seglen, const int W,
-                                               const int K, const int sb, uint32_t *__restrict__ out,
-                                               const uint32_t *__restrict__ oo, DevState *state,
+                                               const int K, const int sb, uint32_t *__restrict__ out, DevState *state,
                                                const int lane, const int warp, const long long t2)
 {
-    static_assert(!(HAS_K && TWO), "the chain limit is only implemented for the single list");
     enum { ST_IDLE = 0, ST_SEEK = 1, ST_WALK = 2, ST_CAND = 3, ST_DONE = 4, ST_FIN = 5, ST_HEAVY = 6, ST_LONG = 7 };
-    const uint32_t ngrp = HASH_SIZE >> sb;
+        const uint32_t ngrp = HASH_SIZE >> sb;
     /* first filter of a walk: 4 bytes when the buckets are split (the walk only looks for matches
      * of >= 4, the trigram sweep does the rest), the trigram otherwise */
     const uint32_t fmask0 = sb ? 0xFFFFFFFFu : 0xFFFFFFu;
@@ -43,38 +32,33 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
     uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
     uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
     asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
-    const uint32_t lbase_old = lbase + 2 * RUN_BLK;
     const int nchunks = (seglen + MATCH_CHUNK - 1) / MATCH_CHUNK;
     int st = ST_IDLE;
     int i = 0, p = 0, q = 0, k = 0, k_lo = 0, k_hi = 0, best_len = 2, best_dist = 0, maxlen = 0, hops = 0;
     uint32_t pw0 = 0, pw1 = 0, fword = 0, fmask = 0;
-    uint32_t ow = 0;     /* TWO: the bucket's range in the window block's list (slots relative to RUN_BLK); OW_DONE once the walk is in it */
     int foff = 0;
-    constexpr uint32_t OW_DONE = 0xFFFFFFFFu; /* (no bucket ends at slot 65535 and starts at 65535) */
-    (void)hops; (void)ow; (void)lbase_old;
 
     /* take position i_ as a parse head (caller has claimed it) */
 #define INIT_HEAD(i_)                                                                   \
-    do {                                                                                \
-        i = (i_);                                                                       \
-        p = hist + i;                                                                   \
-        maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;               \
-        best_len = 2; best_dist = 0; hops = 0;                                          \
-        if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                                   \
-        else {                                                                          \
-            pw0 = ld4s(dbase + p);                                                      \
+    do {                                                                            \
+        i = (i_);                                                                   \
+        p = hist + i;                                                               \
+        maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;           \
+        best_len = 2; best_dist = 0; hops = 0;                                      \
+        if (maxlen < DFL_MIN_MATCH) { st = ST_DONE; }                               \
+        else {                                                                      \
+            pw0 = ld4s(dbase + p);                                                  \
             if (sb && maxlen == DFL_MIN_MATCH) { st = ST_DONE; } /* split buckets: only the trigram sweep applies */ \
-            else {                                                                      \
-                st = ST_SEEK;                                                           \
-                pw1 = ld4s(dbase + p + 4);                                              \
-                foff = 0; fmask = fmask0; fword = pw0 & fmask0;                         \
-                const uint32_t b_ = hash4(pw0, ngrp, sb);                               \
-                if (TWO) ow = OO_LOAD(oo + b_);                                                                    \
-                k_lo = (int)lds_u16(obase + 2 * b_);                                    \
-                k = k_lo;                                                               \
-                k_hi = (int)lds_u16(obase + 2 * b_ + 2);                                \
-            }                                                                           \
-        }                                                                               \
+            else {                                                                  \
+                st = ST_SEEK;                                                       \
+                pw1 = ld4s(dbase + p + 4);                                          \
+                foff = 0; fmask = fmask0; fword = pw0 & fmask0;                     \
+                const uint32_t b_ = hash4(pw0, ngrp, sb);                           \
+                k_lo = (int)lds_u16(obase + 2 * b_);                                \
+                k = k_lo;                                                           \
+                k_hi = (int)lds_u16(obase + 2 * b_ + 2);                            \
+            }                                                                       \
+        }                                                                           \
     } while (0)
 
 #ifdef DFL_SEARCH_STATS
@@ -105,36 +89,22 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
             } else {
 #pragma unroll 1
                 for (int t = 0; t < HOP_BATCH; t += 2) {
-                    int q1, q2, real2 = 1; /* real2: q2 is a bucket entry (k is only looked at again then) */
-                    if (k - k_lo >= 2) { /* both entries come from the list the walk is in */
-                        q1 = (int)lds_u16(lbase + 2 * k - 2);
-                        q2 = (int)lds_u16(lbase + 2 * k - 4);
-                        k -= 2;
-                    } else {
-                        /* at the end of a list: one entry left, or none.  TWO: the segment block's list is followed by
-                         * the window block's, the hand-over happens between any two entries (no step is lost to it) */
-                        if (k <= k_lo) {
-                            if (!TWO || ow == OW_DONE) { st = ST_DONE; break; }
-                            k_lo = RUN_BLK + (int)(ow & 0xFFFF); k = RUN_BLK + (int)(ow >> 16); ow = OW_DONE;
-                            if (k <= k_lo) { st = ST_DONE; break; }
-                        }
-                        q1 = (int)lds_u16(lbase + 2 * (--k));
-                        if (TWO && k <= k_lo && ow != OW_DONE) { k_lo = RUN_BLK + (int)(ow & 0xFFFF); k = RUN_BLK + (int)(ow >> 16); ow = OW_DONE; }
-                        if (k > k_lo) q2 = (int)lds_u16(lbase + 2 * (--k));
-                        else { q2 = p - W - 1; real2 = 0; } /* no second entry: reads as "outside the window" */
-                    }
+                    if (k <= k_lo) { st = ST_DONE; break; }
+                    const int q1 = (int)lds_u16(lbase + 2 * (k - 1));
+                    const int q2 = k - 1 > k_lo ? (int)lds_u16(lbase + 2 * (k - 2)) : p - W - 1; /* no second entry: reads as "outside the window" */
                     const uint32_t w1 = ld4s(dbase + q1 + foff), w2 = ld4s(dbase + (q2 < 0 ? 0 : q2) + foff);
 #ifdef DFL_SEARCH_STATS
                     sx_hops += 2;
 #endif
                     const bool o1 = p - q1 > W, h1 = (w1 & fmask) == fword, o2 = p - q2 > W, h2 = (w2 & fmask) == fword;
                     if (o1 | h1 | o2 | h2) { /* one exit; which of the four it was is sorted out off the hot path */
-                        if (o1) { st = ST_DONE; }
-                        else if (h1) { st = ST_CAND; q = q1; k += real2; /* q2 is looked at again */ }
-                        else if (o2) { st = ST_DONE; }
-                        else { st = ST_CAND; q = q2; }
+                        if (o1) { st = ST_DONE; k -= 1; }
+                        else if (h1) { st = ST_CAND; q = q1; k -= 1; }
+                        else if (o2) { st = ST_DONE; k -= 2; }
+                        else { st = ST_CAND; q = q2; k -= 2; }
                         break;
                     }
+                    k -= 2;
                 }
             }
         }
@@ -145,11 +115,6 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
         if (st == ST_WALK) {
             int rem = k - k_lo;
             if (HAS_K && K - hops < rem) rem = K - hops;
-            /* TWO: the window block's part counts too, by the share of that block the head's window still covers */
-            #ifndef REM_SCALED
-#define REM_SCALED 1
-#endif
-            if (TWO && ow != OW_DONE) rem += REM_SCALED ? (int)(((ow >> 16) - (ow & 0xFFFF)) * (uint32_t)(RUN_BLK - i)) >> 15 : (int)((ow >> 16) - (ow & 0xFFFF));
             if (rem > COOP_MIN) st = ST_HEAVY;
         }
         /* phase B: full compare (check_dup_str) for the lanes holding a candidate.  A lane compares up
@@ -233,56 +198,46 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 int hlo = __shfl_sync(FULL, k_lo, L);
                 const int hmax = __shfl_sync(FULL, maxlen, L);
                 const uint32_t hw0 = __shfl_sync(FULL, pw0, L), hw1 = __shfl_sync(FULL, pw1, L);
-                const uint32_t how = TWO ? __shfl_sync(FULL, ow, L) : 0u;
                 const int hhops = HAS_K ? __shfl_sync(FULL, hops, L) : 0;
                 if (HAS_K && hk - (K - hhops) > hlo) hlo = hk - (K - hhops);
                 int hbest = __shfl_sync(FULL, best_len, L), hdist = __shfl_sync(FULL, best_dist, L);
                 int hfoff = hbest == 2 ? 0 : hbest - 3;
                 uint32_t hfmask = hbest == 2 ? fmask0 : 0xFFFFFFFFu;
                 uint32_t hfword = ld4s(dbase + hp + hfoff) & hfmask;
-                bool ended = false; /* the walk is over: best == maxlen, or the rest of the bucket is outside the window */
-                int hk_ = hk, hlo_ = hlo;
-#pragma unroll 1
-                for (int part = 0; part < (TWO ? 2 : 1) && !ended; part++) {
-                    if (TWO && part == 1) { /* then the window block's part of the bucket */
-                        if (how == OW_DONE) break;
-                        hk_ = RUN_BLK + (int)(how >> 16); hlo_ = RUN_BLK + (int)(how & 0xFFFF);
-                    }
-                    for (int top = hk_; top > hlo_; top -= 32) {
-                        const int kk = top - 1 - lane;
-                        bool valid = kk >= hlo_;
-                        const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
-                        valid = valid && (hp - cq <= W);
-                        uint32_t key = valid ? 0x80000000u : 0u;
-                        if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {
-                            int len;
-                            uint32_t x = ld4s(dbase + cq) ^ hw0;
+                for (int top = hk; top > hlo; top -= 32) {
+                    const int kk = top - 1 - lane;
+                    bool valid = kk >= hlo;
+                    const int cq = valid ? (int)lds_u16(lbase + 2 * kk) : 0;
+                    valid = valid && (hp - cq <= W);
+                    uint32_t key = valid ? 0x80000000u : 0u;
+                    if (valid && (ld4s(dbase + cq + hfoff) & hfmask) == hfword) {
+                        int len;
+                        uint32_t x = ld4s(dbase + cq) ^ hw0;
+                        if (x) {
+                            len = (__ffs(x) - 1) >> 3;
+                        } else {
+                            x = ld4s(dbase + cq + 4) ^ hw1;
                             if (x) {
-                                len = (__ffs(x) - 1) >> 3;
+                                len = 4 + ((__ffs(x) - 1) >> 3);
                             } else {
-                                x = ld4s(dbase + cq + 4) ^ hw1;
-                                if (x) {
-                                    len = 4 + ((__ffs(x) - 1) >> 3);
-                                } else {
-                                    len = 8;
-                                    while (len < hmax) {
-                                        x = ld4s(dbase + hp + len) ^ ld4s(dbase + cq + len);
-                                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                                        len += 4;
-                                    }
+                                len = 8;
+                                while (len < hmax) {
+                                    x = ld4s(dbase + hp + len) ^ ld4s(dbase + cq + len);
+                                    if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                                    len += 4;
                                 }
                             }
-                            if (len > hmax) len = hmax;
-                            if (len > hbest) key |= ((uint32_t)len << 16) | (uint32_t)(0xFFFF - (hp - cq));
                         }
-                        const uint32_t kmax = __reduce_max_sync(FULL, key);
-                        if (!(kmax >> 31)) { ended = true; break; } /* the whole pass is outside the window */
-                        if (kmax & 0x7FFFFFFFu) {
-                            hbest = (kmax >> 16) & 0x7FFF;
-                            hdist = 0xFFFF - (kmax & 0xFFFF);
-                            if (hbest == hmax) { ended = true; break; }
-                            hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4s(dbase + hp + hfoff);
-                        }
+                        if (len > hmax) len = hmax;
+                        if (len > hbest) key |= ((uint32_t)len << 16) | (uint32_t)(0xFFFF - (hp - cq));
+                    }
+                    const uint32_t kmax = __reduce_max_sync(FULL, key);
+                    if (!(kmax >> 31)) break; /* the whole pass is outside the window */
+                    if (kmax & 0x7FFFFFFFu) {
+                        hbest = (kmax >> 16) & 0x7FFF;
+                        hdist = 0xFFFF - (kmax & 0xFFFF);
+                        if (hbest == hmax) break;
+                        hfoff = hbest - 3; hfmask = 0xFFFFFFFFu; hfword = ld4s(dbase + hp + hfoff);
                     }
                 }
                 if (lane == L) { best_len = hbest; best_dist = hdist; st = ST_DONE; }
@@ -301,27 +256,18 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 const int hp = __shfl_sync(FULL, p, L);
                 const uint32_t hw = __shfl_sync(FULL, pw0, L) & 0xFFFFFFu;
                 const uint32_t g_ = hash4(hw, ngrp, sb); /* fourth byte 0 -> first bucket of the group */
-                uint32_t og0 = 0, og1 = 0;
-                if (TWO) { og0 = OO_LOAD(oo + g_); og1 = OO_LOAD(oo + g_ + (1 << DFL_SUB_BITS) - 1); } /* in flight during the first sweep */
-                int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
-                uint32_t gl = lbase;
+                const int glo = (int)lds_u16(obase + 2 * g_), ghi = (int)lds_u16(obase + 2 * (g_ + (1 << DFL_SUB_BITS)));
                 uint32_t loc = 0;
-#pragma unroll 1
-                for (int part = 0; part < (TWO ? 2 : 1); part++) {
-                    for (int kk = ghi - 1 - lane; kk >= glo; kk -= 64) { /* two steps' loads in flight together */
-                        const int kb = kk - 32;
-                        const int cq = (int)lds_u16(gl + 2 * kk), cq2 = kb >= glo ? (int)lds_u16(gl + 2 * kb) : hp;
-                        const int d = hp - cq, d2 = hp - cq2;
-                        const bool in1 = (unsigned)(d - 1) < (unsigned)W, in2 = (unsigned)(d2 - 1) < (unsigned)W;
-                        const uint32_t t1 = in1 ? ld4s(dbase + cq) & 0xFFFFFFu : ~hw, t2_ = in2 ? ld4s(dbase + cq2) & 0xFFFFFFu : ~hw;
-                        if (t1 == hw && (uint32_t)cq + 1 > loc) loc = (uint32_t)cq + 1;
-                        if (t2_ == hw && (uint32_t)cq2 + 1 > loc) loc = (uint32_t)cq2 + 1;
-                    }
-                    loc = __reduce_max_sync(FULL, loc);
-                    if (!TWO || loc) break;
-                    /* nothing in the segment block: the window block's part of the group */
-                    gl = lbase_old; glo = (int)(og0 & 0xFFFF); ghi = (int)(og1 >> 16);
+                for (int kk = ghi - 1 - lane; kk >= glo; kk -= 64) { /* two steps' loads in flight together */
+                    const int kb = kk - 32;
+                    const int cq = (int)lds_u16(lbase + 2 * kk), cq2 = kb >= glo ? (int)lds_u16(lbase + 2 * kb) : hp;
+                    const int d = hp - cq, d2 = hp - cq2;
+                    const bool in1 = (unsigned)(d - 1) < (unsigned)W, in2 = (unsigned)(d2 - 1) < (unsigned)W;
+                    const uint32_t t1 = in1 ? ld4s(dbase + cq) & 0xFFFFFFu : ~hw, t2 = in2 ? ld4s(dbase + cq2) & 0xFFFFFFu : ~hw;
+                    if (t1 == hw && (uint32_t)cq + 1 > loc) loc = (uint32_t)cq + 1;
+                    if (t2 == hw && (uint32_t)cq2 + 1 > loc) loc = (uint32_t)cq2 + 1;
                 }
+                loc = __reduce_max_sync(FULL, loc);
                 if (lane == L && loc) { best_len = DFL_MIN_MATCH; best_dist = p - (int)(loc - 1); }
             }
             if (st == ST_DONE) {
@@ -380,8 +326,9 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
         atomicAdd(&state->t_phase[18], sx_hops); atomicAdd(&state->t_phase[19], sx_seek);
         S.scan_w[warp] = (uint32_t)(clock64() - t2); /* when this warp ran out of work */
     }
-#else
-    (void)state; (void)t2;
+#endif
+#ifndef DFL_SEARCH_STATS
+    (void)state; (void)t2; (void)warp;
 #endif
 #undef INIT_HEAD
 }
@@ -390,70 +337,49 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
  * The same search for segments indexed by plain trigram buckets (sb == 0: data with hardly any repetition --
  * ciphertext, compressed payloads; a bucket holds a handful of positions): M(p) for EVERY position of the segment, a
  * thread per list slot, no parse heads, no chains, no claims.  Slot k holds position p; its candidates are the slots
- * before it in its bucket (the segment block's list, nearest first), then, TWO only, the window block's bucket from its
- * newest entry down to the window's edge.  Longest wins, the nearest on ties (strict '>', src/deflate_compress.c:258);
- * k_parse then follows the chain of tokens from position 0.  Positions the index does not hold (the last ones of the
- * input, which have no whole trigram) are literals.
+ * before it in its bucket, nearest first, down to the window's edge.  Longest wins, the nearest on ties (strict '>',
+ * src/deflate_compress.c:258); k_parse then follows the chain of tokens from position 0.  Positions the index does not
+ * hold (the last ones of the input, which have no whole trigram) are literals.
  */
-template <bool TWO>
 __device__ __forceinline__ void search_flat(MatchSmem &S, const uint32_t soff, const int hist, const int seglen, const int W,
-                                            const int ni_seg, const int lofs_seg, uint32_t *__restrict__ out,
-                                            const uint32_t *__restrict__ oo, const int tid)
+                                            const int ni, const int idx_end, uint32_t *__restrict__ out, const int tid)
 {
-    const uint32_t ngrp = HASH_SIZE;
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
     uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
     uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
     asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
-    /* !TWO: the list holds the window's positions too; only the segment's get a token */
-    for (int k = tid; k < ni_seg; k += MATCH_THREADS) {
-        const int p = (int)lds_u16(lbase + 2 * (lofs_seg + k));
+    for (int k = tid; k < ni; k += MATCH_THREADS) {
+        const int p = (int)lds_u16(lbase + 2 * k);
         const int i = p - hist;
-        if (i < 0) continue;
+        if (i < 0) continue; /* a window position: indexed, but gets no token */
         const int maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;
         uint32_t tok = lds_u8(dbase + p);
         if (maxlen >= DFL_MIN_MATCH) {
             const uint32_t pw0 = ld4s(dbase + p);
-            const uint32_t b_ = hash4(pw0, ngrp, 0);
+            const int lo = (int)lds_u16(obase + 2 * hash4(pw0, HASH_SIZE, 0));
             int best_len = 2, best_q = 0;
-            int kk = lofs_seg + k - 1, lo = lofs_seg + (int)lds_u16(obase + 2 * b_);
-#pragma unroll 1
-            for (int part = 0; part < (TWO ? 2 : 1); part++) {
-                for (; kk >= lo; kk--) {
-                    const int q = (int)lds_u16(lbase + 2 * kk);
-                    if (p - q > W) { part = 2; break; } /* everything older is outside the window */
-                    const uint32_t x0 = ld4s(dbase + q) ^ pw0;
-                    if (x0 & 0xFFFFFFu) continue; /* another trigram of the bucket */
-                    int len = 3;
-                    if (!(x0 >> 24)) {
-                        len = 4;
-                        while (len < maxlen) {
-                            const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
-                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                            len += 4;
-                        }
+            for (int kk = k - 1; kk >= lo; kk--) {
+                const int q = (int)lds_u16(lbase + 2 * kk);
+                if (p - q > W) break; /* everything older is outside the window */
+                const uint32_t x0 = ld4s(dbase + q) ^ pw0;
+                if (x0 & 0xFFFFFFu) continue; /* another trigram of the bucket */
+                int len = 3;
+                if (!(x0 >> 24)) {
+                    len = 4;
+                    while (len < maxlen) {
+                        const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
+                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                        len += 4;
                     }
-                    if (len > maxlen) len = maxlen;
-                    if (len > best_len) { best_len = len; best_q = q; }
                 }
-                if (TWO && part == 0 && best_len < maxlen) {
-                    const uint32_t ow = OO_LOAD(oo + b_);
-                    lo = RUN_BLK + (int)(ow & 0xFFFF);
-                    kk = RUN_BLK + (int)(ow >> 16) - 1;
-                } else {
-                    break;
-                }
+                if (len > maxlen) len = maxlen;
+                if (len > best_len) { best_len = len; best_q = q; }
+                if (best_len == maxlen) break;
             }
             if (best_len >= DFL_MIN_MATCH) tok = ((uint32_t)(p - best_q) << 16) | (uint32_t)best_len;
         }
         out[i] = tok;
     }
-    /* positions without a whole trigram in the data: the index does not hold them */
-    for (int i = tid; i < seglen; i += MATCH_THREADS) {
-        const int p = hist + i;
-        bool indexed;
-        if (TWO) indexed = i < ni_seg;
-        else indexed = p < ni_seg; /* !TWO: ni_seg counts all positions of [window | segment] */
-        if (!indexed) out[i] = lds_u8(dbase + p);
-    }
+    /* frame positions from idx_end on have no whole trigram in the data: not in the list, literals */
+    for (int p = (idx_end > hist ? idx_end : hist) + tid; p < hist + seglen; p += MATCH_THREADS) out[p - hist] = lds_u8(dbase + p);
 }
