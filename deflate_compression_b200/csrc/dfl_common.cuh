@@ -30,6 +30,7 @@ struct DevState {
     unsigned long long t_phase[24]; /* k_match SM cycles summed over CTAs: stage-in, build, search, total */
     unsigned int sort_fallbacks;   /* segments whose index had to be rebuilt with the ballot-ranked scatter */
     unsigned int inf_pending;      /* k_inf_resolve: some word is still a pointer */
+    unsigned int run_next, run_done; /* k_match_run: next run of segments to hand out, CTAs that have finished (the last one resets both) */
 };
 
 struct SegArrays {

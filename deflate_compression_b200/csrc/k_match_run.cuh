@@ -63,7 +63,13 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
         __syncthreads();
     };
 
-    for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+    for (;;) {
+        /* runs are handed out by a counter: a CTA that was placed late (or drew cheap segments) does not keep a fixed share */
+        if (tid == 0) S.next_chunk = (int)atomicAdd(&state->run_next, 1u);
+        __syncthreads();
+        const int run = S.next_chunk;
+        __syncthreads();
+        if (run >= nruns) break;
         const int sA = run * run_segs, sB = sA + run_segs < ns ? sA + run_segs : ns; /* segments of this launch */
         int sb = DFL_SUB_BITS;
         int ni_win = 0, w_win = 0; /* the window's block: entries, slot it is saved in */
@@ -250,5 +256,9 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
             }
             __syncthreads(); /* red_a / red_b / scan_w are reused by the next segment */
         }
+    }
+    if (tid == 0 && atomicAdd(&state->run_done, 1u) == gridDim.x - 1) { /* the last CTA out resets the counters for the next launch */
+        state->run_next = 0;
+        state->run_done = 0;
     }
 }

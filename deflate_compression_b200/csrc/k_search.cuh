@@ -348,37 +348,50 @@ __device__ __forceinline__ void search_flat(MatchSmem &S, const uint32_t soff, c
     uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list);
     uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
     asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
-    for (int k = tid; k < ni; k += MATCH_THREADS) {
-        const int p = (int)lds_u16(lbase + 2 * k);
-        const int i = p - hist;
-        if (i < 0) continue; /* a window position: indexed, but gets no token */
-        const int maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;
-        uint32_t tok = lds_u8(dbase + p);
-        if (maxlen >= DFL_MIN_MATCH) {
-            const uint32_t pw0 = ld4s(dbase + p);
-            const int lo = (int)lds_u16(obase + 2 * hash4(pw0, HASH_SIZE, 0));
-            int best_len = 2, best_q = 0;
-            for (int kk = k - 1; kk >= lo; kk--) {
-                const int q = (int)lds_u16(lbase + 2 * kk);
-                if (p - q > W) break; /* everything older is outside the window */
-                const uint32_t x0 = ld4s(dbase + q) ^ pw0;
-                if (x0 & 0xFFFFFFu) continue; /* another trigram of the bucket */
-                int len = 3;
-                if (!(x0 >> 24)) {
-                    len = 4;
-                    while (len < maxlen) {
-                        const uint32_t x = ld4s(dbase + p + len) ^ ld4s(dbase + q + len);
-                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                        len += 4;
-                    }
-                }
-                if (len > maxlen) len = maxlen;
-                if (len > best_len) { best_len = len; best_q = q; }
-                if (best_len == maxlen) break;
-            }
-            if (best_len >= DFL_MIN_MATCH) tok = ((uint32_t)(p - best_q) << 16) | (uint32_t)best_len;
+    /* four slots per thread and round: their list, data and offset loads are in flight together (a thread's own
+     * chain of loads -- slot -> position -> bytes -> bucket offset -> candidate -- is what bounds this loop) */
+    for (int k0 = tid; k0 < ni; k0 += 4 * MATCH_THREADS) {
+        int p[4], lo[4];
+        uint32_t pw[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j * MATCH_THREADS;
+            p[j] = k < ni ? (int)lds_u16(lbase + 2 * k) : -1;
         }
-        out[i] = tok;
+#pragma unroll
+        for (int j = 0; j < 4; j++) pw[j] = ld4s(dbase + (p[j] < 0 ? 0 : p[j]));
+#pragma unroll
+        for (int j = 0; j < 4; j++) lo[j] = (int)lds_u16(obase + 2 * hash4(pw[j], HASH_SIZE, 0));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j * MATCH_THREADS, i = p[j] - hist;
+            if (i < 0) continue; /* no slot, or a window position: indexed, but gets no token */
+            const int maxlen = seglen - i < DFL_MAX_MATCH ? seglen - i : DFL_MAX_MATCH;
+            uint32_t tok = pw[j] & 0xFF;
+            if (maxlen >= DFL_MIN_MATCH) {
+                int best_len = 2, best_q = 0;
+                for (int kk = k - 1; kk >= lo[j]; kk--) {
+                    const int q = (int)lds_u16(lbase + 2 * kk);
+                    if (p[j] - q > W) break; /* everything older is outside the window */
+                    const uint32_t x0 = ld4s(dbase + q) ^ pw[j];
+                    if (x0 & 0xFFFFFFu) continue; /* another trigram of the bucket */
+                    int len = 3;
+                    if (!(x0 >> 24)) {
+                        len = 4;
+                        while (len < maxlen) {
+                            const uint32_t x = ld4s(dbase + p[j] + len) ^ ld4s(dbase + q + len);
+                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                            len += 4;
+                        }
+                    }
+                    if (len > maxlen) len = maxlen;
+                    if (len > best_len) { best_len = len; best_q = q; }
+                    if (best_len == maxlen) break;
+                }
+                if (best_len >= DFL_MIN_MATCH) tok = ((uint32_t)(p[j] - best_q) << 16) | (uint32_t)best_len;
+            }
+            out[i] = tok;
+        }
     }
     /* frame positions from idx_end on have no whole trigram in the data: not in the list, literals */
     for (int p = (idx_end > hist ? idx_end : hist) + tid; p < hist + seglen; p += MATCH_THREADS) out[p - hist] = lds_u8(dbase + p);
