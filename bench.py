@@ -385,7 +385,7 @@ def run_gpu(args) -> None:
     comp.enable_timing(True)
     cap = comp.bound(n)
     # two output buffers: the gather of step k (NCCL, its own stream) overlaps the kernels of step k + 1
-    d_outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2 if world > 1 else 1)]
+    d_outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
     d_out = d_outs[0]
     stream = torch.cuda.current_stream().cuda_stream
     is_final = rank == world - 1
@@ -397,35 +397,68 @@ def run_gpu(args) -> None:
     last_gather = {}
 
     def drain(b=None):
+        """Buffer b's transfer (or both) has landed, as far as buffer b's stream is concerned; drain() without an
+        argument also joins the second stream into the current one, where the clock's events are recorded."""
         for k in ((0, 1) if b is None else (b,)):
             if pending[k] is not None:
-                for q in pending[k]:
-                    q.wait()
+                with torch.cuda.stream(tstreams[k]):
+                    for q in pending[k]:
+                        q.wait()
                 pending[k] = None
+        if b is None:
+            torch.cuda.current_stream().wait_stream(tstreams[1])
+
+    # two contexts on two streams take the steps in turn (a context has one call in flight): step k + 1's kernels are
+    # already enqueued while the host reads step k's size back -- and, for N > 1, exchanges the sizes and posts the transfer
+    comps = [comp, D.Compressor(device=local)]
+    tstreams = [torch.cuda.current_stream(), torch.cuda.Stream(device=dev)]
+    for c in comps:
+        c.enable_timing(True)
+
+    def launch(i: int):
+        b = i & 1
+        drain(b)
+        comps[b].enqueue(d_in, n, hist, is_final, d_outs[b].data_ptr(), cap, tstreams[b].cuda_stream)
+
+    def collect(i: int, with_gather: bool = True):
+        """Sizes of step i (its kernels are done), then the gather of sizes and bytes to rank 0; the transfer itself is
+        left in flight and is waited for before its buffers are used again, or by drain()."""
+        b = i & 1
+        out_len, adler = comps[b].finish(tstreams[b].cuda_stream)
+        if world > 1 and with_gather:
+            with torch.cuda.stream(tstreams[b]):
+                sizes = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+                mine = torch.tensor([out_len, adler], dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(sizes, mine)
+                meta = sizes.tolist()
+                sz = meta[0::2]
+                if rank == 0:
+                    offs = np.concatenate([[0], np.cumsum(sz)])
+                    gbuf = gather_bufs[b]
+                    gbuf[:sz[0]].copy_(d_outs[b][:sz[0]])
+                    ops = [dist.P2POp(dist.irecv, gbuf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
+                    pending[b] = dist.batch_isend_irecv(ops)
+                    last_gather.update(buf=b, sizes=sz, adlers=meta[1::2])
+                else:
+                    pending[b] = dist.batch_isend_irecv([dist.P2POp(dist.isend, d_outs[b][:out_len], 0)])
+        return out_len, adler
 
     def step(i: int = 0, with_gather: bool = True):
-        """One pass of the hot path over the shard (+ gather of sizes and bytes to rank 0; the transfer
-        itself is left in flight and is waited for before its buffers are used again, or by drain())."""
-        b = i & 1 if world > 1 else 0
-        drain(b)
-        comp.enqueue(d_in, n, hist, is_final, d_outs[b].data_ptr(), cap, stream)
-        out_len, adler = comp.finish(stream)
-        if world > 1 and with_gather:
-            sizes = torch.zeros(2 * world, dtype=torch.int64, device=dev)
-            mine = torch.tensor([out_len, adler], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(sizes, mine)
-            meta = sizes.tolist()
-            sz = meta[0::2]
-            if rank == 0:
-                offs = np.concatenate([[0], np.cumsum(sz)])
-                gbuf = gather_bufs[b]
-                gbuf[:sz[0]].copy_(d_outs[b][:sz[0]])
-                ops = [dist.P2POp(dist.irecv, gbuf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
-                pending[b] = dist.batch_isend_irecv(ops)
-                last_gather.update(buf=b, sizes=sz, adlers=meta[1::2])
-            else:
-                pending[b] = dist.batch_isend_irecv([dist.P2POp(dist.isend, d_outs[b][:out_len], 0)])
-        return out_len, adler
+        """One pass of the hot path over the shard, start to finish."""
+        launch(i)
+        return collect(i, with_gather)
+
+    def steps_pipelined(k_steps: int, with_gather: bool = True, record=None):
+        """k_steps passes; step k + 1 is enqueued before step k's size is read back (and exchanged, N > 1)."""
+        res = None
+        launch(0)
+        for k in range(k_steps):
+            if k + 1 < k_steps:
+                launch(k + 1)
+            res = collect(k, with_gather)
+            if record is not None:
+                record.append(comps[k & 1].kernel_ms()["k_match"])
+        return res
 
     def sync():
         if world > 1:
@@ -436,7 +469,7 @@ def run_gpu(args) -> None:
     for k in range(args.warmup):
         out_len, adler = step(k)
     drain()
-    launches0 = comp.kernel_launches()
+    launches0 = sum(c.kernel_launches() for c in comps)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -446,18 +479,16 @@ def run_gpu(args) -> None:
     k_match_ms = []
     t0 = time.perf_counter()
     e0.record()
-    for k in range(args.steps):
-        out_len, adler = step(k)
-        k_match_ms.append(comp.kernel_ms()["k_match"])
+    out_len, adler = steps_pipelined(args.steps, record=k_match_ms)
     drain()  # every step's bytes have arrived on rank 0 before the clock stops
     e1.record()
     sync()
     t1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
-    launches = comp.kernel_launches() - launches0
+    launches = sum(c.kernel_launches() for c in comps) - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    kernel_ms = comp.kernel_ms()
-    timed_buf = (args.steps - 1) & 1 if world > 1 else 0   # the buffer the last timed step wrote
+    kernel_ms = comps[(args.steps - 1) & 1].kernel_ms()
+    timed_out = d_outs[(args.steps - 1) & 1]  # the buffer the last timed step wrote
 
     # ---- what the timed loop produced, checked outside the timed region ----
     import hashlib
@@ -466,7 +497,7 @@ def run_gpu(args) -> None:
     digest = hashlib.blake2b(host[hist:].tobytes(), digest_size=16).digest()
     roundtrip_ok, roundtrip_what = None, None
     if world == 1:
-        timed_body = d_outs[0][:out_len].cpu().numpy().tobytes()
+        timed_body = timed_out[:out_len].cpu().numpy().tobytes()
         timed_stream = b"\x78\x9c" + timed_body + int(adler).to_bytes(4, "big")
         roundtrip_ok = zlib.decompress(timed_stream) == host[hist:].tobytes()
         roundtrip_what = "zlib.decompress(header + the body the last timed step left in HBM + its Adler-32) == the corpus"
@@ -501,11 +532,12 @@ def run_gpu(args) -> None:
 
     # compress-only (no gather) for N > 1
     ms_nogather = ms
+    drain()
     if world > 1:
         sync()
         e0.record()
-        for k in range(args.steps):
-            step(k, with_gather=False)
+        steps_pipelined(args.steps, with_gather=False)
+        drain()
         e1.record()
         sync()
         ms_nogather = e0.elapsed_time(e1)
@@ -565,7 +597,7 @@ def run_gpu(args) -> None:
     n_total, out_total = tot.tolist()
 
     peak, peak_src = measured_peak()
-    del d_outs, d_out, gather_bufs
+    del d_outs, d_out, gather_bufs, timed_out
     torch.cuda.empty_cache()
     others = None
     if not args.no_other_workloads:
@@ -582,7 +614,7 @@ def run_gpu(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "256 MiB order-2 Markov text per GPU (BASELINE configs[1], seed 2, 32 MiB stripes)",
                        "window": WINDOW, "segment_bytes": 32768, "chain_limit": 0, "block_mode": "cheapest (all dynamic)",
-                       "l2": "inputs larger than L2 (256 MiB per step)", "sharding": f"contiguous, {world} rank(s)",
+                       "l2": "inputs larger than L2 (256 MiB per step)", "steps_overlap": "two contexts on two streams take the steps in turn; step k + 1 is enqueued while step k's size is read back", "sharding": f"contiguous, {world} rank(s)",
                        "cpu_binding": binding},
             "compression_ratio": n_total / out_total,
             "roundtrip_ok": roundtrip_ok,
