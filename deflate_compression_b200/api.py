@@ -48,6 +48,7 @@ class DflSegInfo(C.Structure):
         ("tree_bits", C.c_int64),
         ("ll_bits", C.c_int64),
         ("d_bits", C.c_int64),
+        ("nblocks", C.c_int64),
     ]
 
 

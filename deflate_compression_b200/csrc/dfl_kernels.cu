@@ -52,6 +52,9 @@ struct dfl_ctx {
     uint16_t *scratch; /* k_match radix-sort ping buffer, one slot per SM */
     SegArrays A;
     void *seg_blob;
+    SplitArrays X;     /* block_mode 4: per-block arrays (X.nblk == NULL otherwise) */
+    void *split_blob;
+    size_t split_segs;
     DevState *state;
     DevState *h_state; /* pinned */
     /* host-buffer path */
@@ -135,7 +138,7 @@ static int check_params(const dfl_params *p)
     if (p->window < 1 || p->window > DFL_MAX_WINDOW) return DFL_E_RANGE;
     if (p->seg_bytes < 1 || p->seg_bytes > DFL_MAX_SEG) return DFL_E_RANGE;
     if (p->chain_limit < 0) return DFL_E_RANGE;
-    if (p->block_mode < 0 || p->block_mode > 3) return DFL_E_RANGE;
+    if (p->block_mode < 0 || p->block_mode > 4) return DFL_E_RANGE;
     return DFL_OK;
 }
 
@@ -144,7 +147,9 @@ extern "C" size_t dfl_b200_bound(const dfl_params *prm, size_t n)
     size_t nseg = n ? (n + prm->seg_bytes - 1) / prm->seg_bytes : 0;
     size_t b = n + nseg * (5 * ((prm->seg_bytes + 65534) / 65535) + 5 + 8) + 64;
     /* a forced fixed/dynamic block may expand: <= 15 bits per literal + header */
-    if (prm->block_mode >= 2) b = 2 * n + nseg * 640 + 64;
+    if (prm->block_mode == 2 || prm->block_mode == 3) b = 2 * n + nseg * 640 + 64;
+    /* a split segment never takes more bits than the same segment as one block; a stored block inside it may pad */
+    if (prm->block_mode == 4) b += nseg * 6 * DFL_SUB_MAX;
     return b;
 }
 
@@ -157,6 +162,10 @@ static void free_ws(dfl_ctx *ctx)
     ctx->tokcand = NULL;
     ctx->seg_blob = NULL;
     ctx->ws_segs = 0;
+    if (ctx->split_blob) cudaFree(ctx->split_blob);
+    ctx->split_blob = NULL;
+    ctx->split_segs = 0;
+    memset(&ctx->X, 0, sizeof(ctx->X));
 }
 
 /* grow-only device buffer of the context */
@@ -184,9 +193,35 @@ static int ensure_index(dfl_ctx *ctx, size_t nseg)
     return DFL_OK;
 }
 
+/* per-block arrays of block_mode 4, made the first time a context splits */
+static int ensure_split(dfl_ctx *ctx, size_t ns)
+{
+    if (ctx->split_segs >= ns) return DFL_OK;
+    if (ctx->split_blob) cudaFree(ctx->split_blob);
+    ctx->split_blob = NULL;
+    ctx->split_segs = 0;
+    const size_t nb = ns * DFL_SUB_MAX;
+    CK(cudaMalloc(&ctx->split_blob, ns * 4 + nb * (6 + LLS + DS + HDR_WORDS) * sizeof(uint32_t) + 256));
+    uint32_t *p = (uint32_t *)ctx->split_blob;
+    SplitArrays &X = ctx->X;
+    X.nblk = p; p += ns;
+    X.btype = p; p += nb;
+    X.hdr_bits = p; p += nb;
+    X.tok0 = p; p += nb;
+    X.ntok = p; p += nb;
+    X.pos0 = p; p += nb;
+    X.nbytes = p; p += nb;
+    X.lltab = p; p += nb * LLS;
+    X.dtab = p; p += nb * DS;
+    X.hdr = p; p += nb * HDR_WORDS;
+    ctx->split_segs = ns;
+    return DFL_OK;
+}
+
 static int ensure_ws(dfl_ctx *ctx, size_t nseg_chunk)
 {
-    if (ctx->ws_segs >= nseg_chunk && ctx->ws_seg_bytes == (size_t)ctx->prm.seg_bytes) return DFL_OK;
+    if (ctx->ws_segs >= nseg_chunk && ctx->ws_seg_bytes == (size_t)ctx->prm.seg_bytes)
+        return ctx->prm.block_mode == 4 ? ensure_split(ctx, ctx->ws_segs) : DFL_OK;
     free_ws(ctx);
     size_t ns = nseg_chunk;
     CK(cudaMalloc(&ctx->tokcand, ns * ctx->prm.seg_bytes * sizeof(uint32_t)));
@@ -210,7 +245,7 @@ static int ensure_ws(dfl_ctx *ctx, size_t nseg_chunk)
     A.cost = (uint32_t *)p; p += ns * 8;
     ctx->ws_segs = ns;
     ctx->ws_seg_bytes = ctx->prm.seg_bytes;
-    return DFL_OK;
+    return ctx->prm.block_mode == 4 ? ensure_split(ctx, ns) : DFL_OK;
 }
 
 extern "C" int dfl_b200_create(dfl_ctx **out, int device, const dfl_params *prm)
@@ -416,14 +451,21 @@ static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist
     else
         LAUNCH(K_PARSE, k_parse, ns, PARSE_THREADS, sizeof(ParseSmem), st, (long long)n, (long long)s0, prm, ctx->tokcand,
                ctx->tokens, ctx->A);
-    LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
-           (long long)s0, ns, prm, ctx->A);
+    SplitArrays X;
+    memset(&X, 0, sizeof(X));
+    if (prm.block_mode == 4) {
+        X = ctx->X;
+        LAUNCH(K_HUFF, k_huff_split, (ns + SPLIT_WARPS - 1) / SPLIT_WARPS, SPLIT_WARPS * 32, 0, st, (long long)n,
+               (long long)s0, ns, prm, ctx->tokens, ctx->A, X);
+    } else
+        LAUNCH(K_HUFF, k_huff, (ns + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st, (long long)n,
+               (long long)s0, ns, prm, ctx->A);
     LAUNCH(K_SCAN, k_scan, 1, SCAN_THREADS, 0, st, ns, ctx->A, ctx->state);
     /* segment index: where each segment starts in the body, and (entry nseg) where the body ends so far */
     CK(cudaMemcpyAsync(ctx->seg_index + s0, ctx->A.out_off, (size_t)ns * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(ctx->seg_index + s0 + ns, &ctx->state->total_out, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     LAUNCH(K_EMIT, k_emit, ns, EMIT_THREADS, 0, st, d_in, (long long)n, (long long)s0, (long long)(nseg - 1),
-           is_final, prm, ctx->tokens, ctx->A, d_out, (unsigned long long)out_cap, ctx->state);
+           is_final, prm, ctx->tokens, ctx->A, X, d_out, (unsigned long long)out_cap, ctx->state);
     return DFL_OK;
 }
 
@@ -660,14 +702,15 @@ extern "C" unsigned long long dfl_b200_phase_cycles(dfl_ctx *ctx, int k)
 extern "C" int dfl_b200_seg_info(dfl_ctx *ctx, long seg, dfl_seg_info *info)
 {
     if (!ctx || !info || seg < 0 || seg >= ctx->nseg_kept) return DFL_E_RANGE;
-    info->btype = (int32_t)ctx->h_btype[seg];
+    info->btype = (int32_t)(ctx->h_btype[seg] & 0xFF);
+    info->nblocks = (int64_t)(ctx->h_btype[seg] >> 8 ? ctx->h_btype[seg] >> 8 : 1);
     info->ntokens = (int32_t)ctx->h_ntok[seg];
     info->block_bits = (int64_t)ctx->h_block_bits[seg];
     info->out_bytes = (int64_t)ctx->h_out_bytes[seg];
     info->out_offset = (int64_t)ctx->h_out_off[seg];
     info->tree_bits = (int64_t)ctx->h_cost[2 * seg];
     info->d_bits = (int64_t)ctx->h_cost[2 * seg + 1];
-    info->ll_bits = info->block_bits - 3 - info->tree_bits - info->d_bits;
+    info->ll_bits = info->block_bits - 3 * info->nblocks - info->tree_bits - info->d_bits;
     return DFL_OK;
 }
 

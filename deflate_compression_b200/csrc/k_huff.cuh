@@ -147,25 +147,22 @@ struct BitW {
     }
 };
 
-/*
- * One warp per segment: code construction + exact block costs + choice.
- * Twin of orc_emit_segment's front half (oracle/deflate_oracle.c); what the
- * reference accounts per token in h_tree_d_lens / h_tree_builder_*
- * (src/h_tree.c:75-148, :242-302) is done once per block here.
- */
-__global__ void __launch_bounds__(HUFF_WARPS * 32)
-k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
-{
-    __shared__ HuffSmem s_all[HUFF_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sl = blockIdx.x * HUFF_WARPS + warp;
-    if (sl >= nseg) return;
-    HuffSmem &S = s_all[warp];
-    const long long seg_lo = (seg0 + sl) * prm.seg_bytes;
-    const long long seglen = ((seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n) - seg_lo;
+/* what huff_plan decided for one block (uniform across the warp) */
+struct HuffPlan {
+    int btype;                       /* 0 stored, 1 fixed, 2 dynamic */
+    unsigned long long block_bits;   /* bits of the chosen block incl. its 3 header bits (stored: 8 * (bytes + 5 per 65535)) */
+    uint32_t hdr_bits;               /* bits packed into S.hdr (0 for stored) */
+    uint32_t tree_bits, d_bits;      /* cost split of the chosen block: code description, distance symbols + extra bits */
+};
 
-    for (int i = lane; i < LLS; i += 32) S.ll_freq[i] = i < NLL ? A.ll_freq[(size_t)sl * LLS + i] : 0;
-    S.d_freq[lane] = lane < ND ? A.d_freq[(size_t)sl * DS + lane] : 0;
+/*
+ * Code construction + exact block costs + choice for ONE block whose lit/len and distance counts (EOB included) are in
+ * S.ll_freq / S.d_freq, by one warp.  Leaves the chosen block's packed header in S.hdr and, for a dynamic block, its
+ * codes in S.ll_code / S.d_code.  Twin of orc_plan_block (oracle/deflate_oracle.c); what the reference accounts per
+ * token in h_tree_d_lens / h_tree_builder_* (src/h_tree.c:75-148, :242-302) is done once per block here.
+ */
+__device__ HuffPlan huff_plan(HuffSmem &S, const int lane, const unsigned long long extra, const long long nbytes, const int block_mode)
+{
     S.cl_freq[lane] = 0;
     for (int i = lane; i < HDR_WORDS; i += 32) S.hdr[i] = 0;
     __syncwarp();
@@ -242,23 +239,24 @@ k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
         fix += __shfl_xor_sync(FULL, fix, o);
         tree += __shfl_xor_sync(FULL, tree, o);
     }
-    int btype = 0;
-    unsigned long long block_bits = 0;
+    HuffPlan P;
+    P.btype = 0; P.block_bits = 0; P.hdr_bits = 0; P.tree_bits = 0; P.d_bits = 0;
     if (lane == 0) {
+        int btype;
         for (hclen = 19; hclen > 4 && S.cl_len[c_cl_order[hclen - 1]] == 0; hclen--) {}
-        unsigned long long extra = A.extra[sl];
         dyn += 3 + 5 + 5 + 4 + 3 * hclen + extra;
         fix += 3 + extra;
-        unsigned long long nstored = (unsigned long long)((seglen + 65534) / 65535);
+        unsigned long long nstored = (unsigned long long)((nbytes + 65534) / 65535);
         if (nstored < 1) nstored = 1;
-        unsigned long long stored = 8ull * ((unsigned long long)seglen + 5 * nstored);
-        if (prm.block_mode == 1) btype = 0;
-        else if (prm.block_mode == 2) btype = 1;
-        else if (prm.block_mode == 3) btype = 2;
+        unsigned long long stored = 8ull * ((unsigned long long)nbytes + 5 * nstored);
+        if (block_mode == 1) btype = 0;
+        else if (block_mode == 2) btype = 1;
+        else if (block_mode == 3) btype = 2;
         else if (stored <= fix && stored <= dyn) btype = 0;
         else if (fix <= dyn) btype = 1;
         else btype = 2;
-        block_bits = btype == 0 ? stored : btype == 1 ? fix : dyn;
+        P.btype = btype;
+        P.block_bits = btype == 0 ? stored : btype == 1 ? fix : dyn;
 
         BitW bw{S.hdr, 0};
         if (btype == 2) {
@@ -282,29 +280,211 @@ k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
             bw.put(0, 1);
             bw.put(1, 2);
         }
-        A.hdr_bits[sl] = bw.nbits;
-        A.cost[2 * (size_t)sl] = btype == 2 ? (uint32_t)(tree + 5 + 5 + 4 + 3 * hclen) : 0u;
-        A.cost[2 * (size_t)sl + 1] = btype == 2 ? d_dyn : btype == 1 ? d_fix : 0u;
-        A.btype[sl] = btype;
-        A.block_bits[sl] = block_bits;
-        A.out_bytes[sl] = btype == 0 ? (uint32_t)(seglen + 5 * nstored + 5)
-                                     : (uint32_t)((block_bits + 3 + 7) / 8 + 4);
+        P.hdr_bits = bw.nbits;
+        P.tree_bits = btype == 2 ? (uint32_t)(tree + 5 + 5 + 4 + 3 * hclen) : 0u;
+        P.d_bits = btype == 2 ? d_dyn : btype == 1 ? d_fix : 0u;
     }
-    btype = __shfl_sync(FULL, btype, 0);
+    P.btype = __shfl_sync(FULL, P.btype, 0);
+    P.block_bits = __shfl_sync(FULL, P.block_bits, 0);
+    P.hdr_bits = __shfl_sync(FULL, P.hdr_bits, 0);
+    P.tree_bits = __shfl_sync(FULL, P.tree_bits, 0);
+    P.d_bits = __shfl_sync(FULL, P.d_bits, 0);
     __syncwarp();
+    return P;
+}
+
+/* the planned block's code tables (code_rev | len << 16) and packed header, to the arrays k_emit reads */
+__device__ void huff_store(const HuffSmem &S, const int lane, const int btype, uint32_t *lltab, uint32_t *dtab, uint32_t *hdr)
+{
     if (btype == 2) {
         for (int s = lane; s < LLS; s += 32)
-            A.lltab[(size_t)sl * LLS + s] = s < NLL ? (uint32_t)S.ll_code[s] | ((uint32_t)S.ll_len[s] << 16) : 0;
-        A.dtab[(size_t)sl * DS + lane] = lane < ND ? (uint32_t)S.d_code[lane] | ((uint32_t)S.d_len[lane] << 16) : 0;
-        for (int i = lane; i < HDR_WORDS; i += 32) A.hdr[(size_t)sl * HDR_WORDS + i] = S.hdr[i];
+            lltab[s] = s < NLL ? (uint32_t)S.ll_code[s] | ((uint32_t)S.ll_len[s] << 16) : 0;
+        dtab[lane] = lane < ND ? (uint32_t)S.d_code[lane] | ((uint32_t)S.d_len[lane] << 16) : 0;
+        for (int i = lane; i < HDR_WORDS; i += 32) hdr[i] = S.hdr[i];
     } else if (btype == 1) {
         /* fixed code of RFC 1951 3.2.6 */
         for (int s = lane; s < LLS; s += 32) {
             int l = fixed_ll_len(s);
             uint32_t code = s < 144 ? 0x30 + s : s < 256 ? 0x190 + (s - 144) : s < 280 ? (s - 256) : 0xC0 + (s - 280);
-            A.lltab[(size_t)sl * LLS + s] = (__brev(code) >> (32 - l)) | ((uint32_t)l << 16);
+            lltab[s] = (__brev(code) >> (32 - l)) | ((uint32_t)l << 16);
         }
-        A.dtab[(size_t)sl * DS + lane] = (__brev((uint32_t)lane) >> 27) | (5u << 16);
-        if (lane == 0) A.hdr[(size_t)sl * HDR_WORDS] = S.hdr[0];
+        dtab[lane] = (__brev((uint32_t)lane) >> 27) | (5u << 16);
+        if (lane == 0) hdr[0] = S.hdr[0];
+    }
+}
+
+/* One warp per segment, one block per segment (block_mode 0..3). */
+__global__ void __launch_bounds__(HUFF_WARPS * 32)
+k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
+{
+    __shared__ HuffSmem s_all[HUFF_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = blockIdx.x * HUFF_WARPS + warp;
+    if (sl >= nseg) return;
+    HuffSmem &S = s_all[warp];
+    const long long seg_lo = (seg0 + sl) * prm.seg_bytes;
+    const long long seglen = ((seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n) - seg_lo;
+
+    for (int i = lane; i < LLS; i += 32) S.ll_freq[i] = i < NLL ? A.ll_freq[(size_t)sl * LLS + i] : 0;
+    S.d_freq[lane] = lane < ND ? A.d_freq[(size_t)sl * DS + lane] : 0;
+    __syncwarp();
+    const HuffPlan P = huff_plan(S, lane, A.extra[sl], seglen, prm.block_mode);
+    if (lane == 0) {
+        unsigned long long nstored = (unsigned long long)((seglen + 65534) / 65535);
+        if (nstored < 1) nstored = 1;
+        A.hdr_bits[sl] = P.hdr_bits;
+        A.cost[2 * (size_t)sl] = P.tree_bits;
+        A.cost[2 * (size_t)sl + 1] = P.d_bits;
+        A.btype[sl] = P.btype;
+        A.block_bits[sl] = P.block_bits;
+        A.out_bytes[sl] = P.btype == 0 ? (uint32_t)(seglen + 5 * nstored + 5)
+                                       : (uint32_t)((P.block_bits + 3 + 7) / 8 + 4);
+    }
+    huff_store(S, lane, P.btype, A.lltab + (size_t)sl * LLS, A.dtab + (size_t)sl * DS, A.hdr + (size_t)sl * HDR_WORDS);
+}
+
+/* ------------------------------------------------------------------------- */
+/* k_huff_split: adaptive block splitting (block_mode 4)                     */
+/* ------------------------------------------------------------------------- */
+
+#define SPLIT_WARPS 2
+
+/* per-block arrays of a chunk in block_mode 4 (block b of segment sl at index sl * DFL_SUB_MAX + b) */
+struct SplitArrays {
+    uint32_t *nblk;                 /* [nseg] blocks of the segment; NULL = not splitting */
+    uint32_t *btype, *hdr_bits;     /* [nseg * DFL_SUB_MAX] */
+    uint32_t *tok0, *ntok;          /* the block's tokens: first index in the segment's token array, count */
+    uint32_t *pos0, *nbytes;        /* the input bytes it covers (stored blocks copy them) */
+    uint32_t *lltab, *dtab, *hdr;   /* [nseg * DFL_SUB_MAX][LLS | DS | HDR_WORDS] */
+};
+
+struct SplitSmem {
+    HuffSmem H;
+    uint32_t sub_ll[DFL_SUB_MAX][LLS], sub_d[DFL_SUB_MAX][DS];
+    uint32_t sub_extra[DFL_SUB_MAX];
+    uint32_t tok_start[DFL_SUB_MAX + 1], pos_start[DFL_SUB_MAX + 1];
+};
+
+/*
+ * One warp per segment.  Adaptive block splitting, the reference's stated aim (README.md:15-20: "how to divide the data
+ * up into chunks, each able to have its own Huffman coding"; its running-cost machinery, src/aht.c:239-277, never
+ * reaches a decision).  Twin of orc_emit_segment / orc_split_range (oracle/deflate_oracle.c): the segment's tokens are
+ * cut where they cross multiples of DFL_SUB_BYTES input bytes; the warp histograms the sub-blocks in shared memory,
+ * then bisects a range of sub-blocks whenever its two halves, each as its own cheapest block (exact costs, huff_plan),
+ * take strictly fewer bits than the range as one block.  The token stream is untouched.
+ */
+__global__ void __launch_bounds__(SPLIT_WARPS * 32)
+k_huff_split(long long n, long long seg0, int nseg, dfl_params prm, const uint32_t *__restrict__ tokens, SegArrays A, SplitArrays X)
+{
+    __shared__ SplitSmem s_all[SPLIT_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = blockIdx.x * SPLIT_WARPS + warp;
+    if (sl >= nseg) return;
+    SplitSmem &S = s_all[warp];
+    const long long seg_lo = (seg0 + sl) * prm.seg_bytes;
+    const int seglen = (int)(((seg_lo + prm.seg_bytes < n) ? seg_lo + prm.seg_bytes : n) - seg_lo);
+    const int ntok = (int)A.ntok[sl];
+    const uint32_t *tc = tokens + (size_t)sl * prm.seg_bytes;
+    const int nsub = seglen > DFL_SUB_BYTES ? (seglen + DFL_SUB_BYTES - 1) / DFL_SUB_BYTES : 1;
+
+    /* ---- sub-block histograms, first token and first byte of every sub-block ---- */
+    for (int i = lane; i < DFL_SUB_MAX * LLS; i += 32) (&S.sub_ll[0][0])[i] = 0;
+    for (int i = lane; i < DFL_SUB_MAX * DS; i += 32) (&S.sub_d[0][0])[i] = 0;
+    if (lane < DFL_SUB_MAX) S.sub_extra[lane] = 0;
+    if (lane <= DFL_SUB_MAX) { S.tok_start[lane] = lane ? (uint32_t)ntok : 0u; S.pos_start[lane] = lane ? (uint32_t)seglen : 0u; }
+    __syncwarp();
+    int pos = 0, prev_sub = 0;
+    for (int base = 0; base < ntok; base += 32) {
+        const int k = base + lane;
+        const uint32_t t = k < ntok ? tc[k] : 0u;
+        const int adv = k < ntok ? ((t >> 16) ? (int)(t & 0xFFFF) : 1) : 0;
+        int x = adv;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        const int mypos = pos + x - adv;
+        const int sub = nsub > 1 ? mypos / DFL_SUB_BYTES : 0;
+        int before = __shfl_up_sync(FULL, sub, 1);
+        if (lane == 0) before = prev_sub;
+        if (k < ntok) {
+            if (sub != before) { S.tok_start[sub] = (uint32_t)k; S.pos_start[sub] = (uint32_t)mypos; } /* (a token is shorter than a sub-block) */
+            if ((t >> 16) == 0) {
+                atomicAdd(&S.sub_ll[sub][t & 0xFF], 1u);
+            } else {
+                int eb, ev, e2;
+                atomicAdd(&S.sub_ll[sub][len_sym((int)(t & 0xFFFF), eb, ev)], 1u);
+                atomicAdd(&S.sub_d[sub][dist_sym((int)(t >> 16), e2, ev)], 1u);
+                atomicAdd(&S.sub_extra[sub], (uint32_t)(eb + e2));
+            }
+        }
+        pos += __shfl_sync(FULL, x, 31);
+        const int nlast = ntok - base < 32 ? ntok - base : 32;
+        prev_sub = __shfl_sync(FULL, sub, nlast - 1);
+    }
+    __syncwarp();
+
+    /* a block over sub-blocks [a, b): counts summed into the plan's tables, one EOB */
+    auto plan_range = [&](int a, int b) -> HuffPlan {
+        for (int s = lane; s < LLS; s += 32) {
+            uint32_t f = s == 256 ? 1u : 0u;
+            for (int j = a; j < b; j++) f += S.sub_ll[j][s];
+            S.H.ll_freq[s] = s < NLL ? f : 0u;
+        }
+        uint32_t fd = 0, ex = lane >= a && lane < b ? S.sub_extra[lane] : 0u;
+        for (int j = a; j < b; j++) fd += S.sub_d[j][lane];
+        S.H.d_freq[lane] = lane < ND ? fd : 0u;
+        ex = __reduce_add_sync(FULL, ex);
+        __syncwarp();
+        return huff_plan(S.H, lane, ex, (long long)S.pos_start[b] - (long long)S.pos_start[a], prm.block_mode == 4 ? 0 : prm.block_mode);
+    };
+
+    /* ---- top-down bisection (explicit stack: ranges still to be looked at, leftmost on top) ---- */
+    int st_a[4], st_b[4], sp = 0;
+    st_a[0] = 0; st_b[0] = nsub; sp = 1;
+    uint32_t nblk = 0, tree_sum = 0, d_sum = 0, first_type = 0;
+    unsigned long long bits_sum = 0, run_bits = 0; /* costs as planned; exact bits of the segment's stream so far */
+    while (sp > 0) {
+        sp--;
+        const int a = st_a[sp], b = st_b[sp];
+        if (b - a >= 2) {
+            const int mid = (a + b) / 2;
+            const HuffPlan L = plan_range(a, mid), R = plan_range(mid, b);
+            const HuffPlan W = plan_range(a, b);
+            if (L.block_bits + R.block_bits < W.block_bits) {
+                st_a[sp] = mid; st_b[sp] = b; sp++;
+                st_a[sp] = a; st_b[sp] = mid; sp++;
+                continue;
+            }
+        }
+        const HuffPlan P = plan_range(a, b); /* (for a range just declined this repeats W: the plan's tables are the last one's) */
+        const size_t gb = (size_t)sl * DFL_SUB_MAX + nblk;
+        const uint32_t nb = S.pos_start[b] - S.pos_start[a];
+        if (lane == 0) {
+            X.btype[gb] = (uint32_t)P.btype;
+            X.hdr_bits[gb] = P.hdr_bits;
+            X.tok0[gb] = S.tok_start[a];
+            X.ntok[gb] = S.tok_start[b] - S.tok_start[a];
+            X.pos0[gb] = S.pos_start[a];
+            X.nbytes[gb] = nb;
+        }
+        huff_store(S.H, lane, P.btype, X.lltab + gb * LLS, X.dtab + gb * DS, X.hdr + gb * HDR_WORDS);
+        if (nblk == 0) first_type = (uint32_t)P.btype;
+        if (P.btype == 0) run_bits = ((run_bits + 3 + 7) & ~7ull) + 32 + 8ull * nb; /* header bits, padding, LEN / NLEN, the bytes */
+        else run_bits += P.block_bits;
+        bits_sum += P.block_bits;
+        tree_sum += P.tree_bits;
+        d_sum += P.d_bits;
+        nblk++;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        X.nblk[sl] = nblk;
+        A.btype[sl] = first_type | (nblk << 8); /* (the host reads the block count from the upper bits) */
+        A.hdr_bits[sl] = 0;
+        A.cost[2 * (size_t)sl] = tree_sum;
+        A.cost[2 * (size_t)sl + 1] = d_sum;
+        A.block_bits[sl] = bits_sum;
+        A.out_bytes[sl] = (uint32_t)(((run_bits + 3 + 7) >> 3) + 4); /* + the sync marker */
     }
 }

@@ -37,6 +37,8 @@ extern "C" {
 #define DFL_MAX_MATCH 258     /* src/include/deflate.h:4 */
 #define DFL_MAX_WINDOW 32768  /* README.md:6 */
 #define DFL_MAX_SEG 32768     /* one segment = one CTA-resident window pair */
+#define DFL_SUB_BYTES 4096    /* block_mode 4: a segment's tokens are cut where they cross multiples of this many input bytes */
+#define DFL_SUB_MAX 8         /* DFL_MAX_SEG / DFL_SUB_BYTES: blocks a segment can be split into */
 #define DFL_HASH_BUCKETS 15360 /* bucket count (sized to the shared-memory budget); observable only with chain_limit > 0 */
 /* bucket of the 3 bytes packed little-endian in v (low 24 bits): multiplicative hash, range-reduced by mul-hi */
 #define DFL_HASH3(v) ((uint32_t)(((uint64_t)((((uint32_t)(v)) & 0xFFFFFFu) * 0x9E3779B1u) * DFL_HASH_BUCKETS) >> 32))
@@ -67,20 +69,24 @@ typedef struct dfl_params {
     int32_t seg_bytes;   /* 1..32768; independent segment (parse restart, one block + sync marker) */
     int32_t chain_limit; /* 0 = walk the whole chain (reference); K = newest K entries of the 4-byte bucket, then the nearest 3-byte match */
     int32_t use_dict;    /* 1 = segments may match into the preceding <= window bytes */
-    int32_t block_mode;  /* 0 = cheapest of stored/fixed/dynamic; 1/2/3 force stored/fixed/dynamic */
+    int32_t block_mode;  /* 0 = cheapest of stored/fixed/dynamic; 1/2/3 force stored/fixed/dynamic; 4 = cheapest, and a
+                          * segment may be split into up to DFL_SUB_MAX blocks where that saves bits (adaptive block
+                          * splitting, the reference's stated aim: README.md:15-20) */
 } dfl_params;
 
 typedef struct dfl_seg_info {
-    int32_t btype;       /* 0 stored, 1 fixed, 2 dynamic */
+    int32_t btype;       /* 0 stored, 1 fixed, 2 dynamic (block_mode 4: of the segment's first block) */
     int32_t ntokens;
-    int64_t block_bits;  /* chosen block incl. 3 header bits, excl. sync marker */
+    int64_t block_bits;  /* chosen block(s) incl. 3 header bits each, excl. sync marker (a stored block inside a split
+                          * segment counts 8 * (bytes + 5)) */
     int64_t out_bytes;   /* bytes of this segment in the stream incl. sync marker */
     int64_t out_offset;  /* byte offset of the segment in the deflate body */
     /* the block's cost the way struct compress_stats splits it (src/include/deflate_ext.h:19-31);
-     * tree_bits + ll_bits + d_bits + 3 == block_bits */
+     * tree_bits + ll_bits + d_bits + 3 * nblocks == block_bits */
     int64_t tree_bits;   /* code description: HLIT/HDIST/HCLEN, code-length code, run-length coded lengths (0 unless dynamic) */
     int64_t ll_bits;     /* lit/len symbols + length extra bits (stored: everything but the 3 header bits) */
     int64_t d_bits;      /* distance symbols + distance extra bits */
+    int64_t nblocks;     /* blocks the segment was emitted as: 1 unless block_mode 4 split it */
 } dfl_seg_info;
 
 void dfl_b200_default_params(dfl_params *p);

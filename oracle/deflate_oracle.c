@@ -462,69 +462,86 @@ typedef struct {
     int nitems, hlit, hdist, hclen;
 } orc_dyn;
 
-/* Emit one segment: its block(s) then the byte-aligning empty stored block. */
-static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint32_t *tokens,
-                             long ntok, const orc_params *prm, int final_seg, orc_seg_stats *st)
-{
+/* What one block of `ntok` tokens over `n` raw bytes would be: histograms, the dynamic code, exact costs, the choice. */
+typedef struct {
     uint32_t ll_freq[ORC_NUM_LL + 2], d_freq[ORC_NUM_D + 2], cl_freq[ORC_NUM_CL];
     orc_dyn dy;
-    uint8_t seq[ORC_NUM_LL + ORC_NUM_D + 4];
-    int64_t extra_bits = 0, d_extra_bits = 0, fixed_bits, dyn_bits, stored_bits;
-    long k, nstored, start_pos = bw->pos;
-    int s, eb, ev, btype, i;
+    int64_t extra_bits, d_extra_bits, fixed_bits, dyn_bits, stored_bits;
+    int btype;
+} orc_plan;
 
-    memset(ll_freq, 0, sizeof(ll_freq));
-    memset(d_freq, 0, sizeof(d_freq));
-    memset(cl_freq, 0, sizeof(cl_freq));
+static int64_t plan_bits(const orc_plan *pl) { return pl->btype == 0 ? pl->stored_bits : pl->btype == 1 ? pl->fixed_bits : pl->dyn_bits; }
+
+static void orc_plan_block(orc_plan *pl, long n, const uint32_t *tokens, long ntok, int block_mode)
+{
+    uint8_t seq[ORC_NUM_LL + ORC_NUM_D + 4];
+    orc_dyn *dy = &pl->dy;
+    long k, nstored;
+    int s, eb, ev, i;
+
+    memset(pl->ll_freq, 0, sizeof(pl->ll_freq));
+    memset(pl->d_freq, 0, sizeof(pl->d_freq));
+    memset(pl->cl_freq, 0, sizeof(pl->cl_freq));
+    pl->extra_bits = pl->d_extra_bits = 0;
     for (k = 0; k < ntok; k++) {
         uint32_t t = tokens[k];
         if (ORC_TOK_DIST(t) == 0) {
-            ll_freq[t & 0xFF]++;
+            pl->ll_freq[t & 0xFF]++;
         } else {
-            ll_freq[orc_len_sym((int)ORC_TOK_LEN(t), &eb, &ev)]++;
-            extra_bits += eb;
-            d_freq[orc_dist_sym((int)ORC_TOK_DIST(t), &eb, &ev)]++;
-            extra_bits += eb;
-            d_extra_bits += eb;
+            pl->ll_freq[orc_len_sym((int)ORC_TOK_LEN(t), &eb, &ev)]++;
+            pl->extra_bits += eb;
+            pl->d_freq[orc_dist_sym((int)ORC_TOK_DIST(t), &eb, &ev)]++;
+            pl->extra_bits += eb;
+            pl->d_extra_bits += eb;
         }
     }
-    ll_freq[256]++; /* end of block, counted once: src/deflate_compress.c:233-234 */
+    pl->ll_freq[256]++; /* end of block, counted once: src/deflate_compress.c:233-234 */
 
     /* dynamic code (RFC 1951 3.2.7) */
-    orc_huff_lengths(ll_freq, ORC_NUM_LL, 15, dy.ll_len);
-    orc_huff_lengths(d_freq, ORC_NUM_D, 15, dy.d_len);
-    for (dy.hlit = ORC_NUM_LL; dy.hlit > 257 && dy.ll_len[dy.hlit - 1] == 0; dy.hlit--) {}
-    for (dy.hdist = ORC_NUM_D; dy.hdist > 1 && dy.d_len[dy.hdist - 1] == 0; dy.hdist--) {}
-    memcpy(seq, dy.ll_len, (size_t)dy.hlit);
-    memcpy(seq + dy.hlit, dy.d_len, (size_t)dy.hdist);
-    dy.nitems = orc_rle_lengths(seq, dy.hlit + dy.hdist, dy.items);
-    for (i = 0; i < dy.nitems; i++) cl_freq[dy.items[i].sym]++;
-    orc_huff_lengths(cl_freq, ORC_NUM_CL, 7, dy.cl_len);
-    for (dy.hclen = 19; dy.hclen > 4 && dy.cl_len[orc_cl_order[dy.hclen - 1]] == 0; dy.hclen--) {}
-    orc_canonical_codes(dy.ll_len, ORC_NUM_LL, dy.ll_code);
-    orc_canonical_codes(dy.d_len, ORC_NUM_D, dy.d_code);
-    orc_canonical_codes(dy.cl_len, ORC_NUM_CL, dy.cl_code);
+    orc_huff_lengths(pl->ll_freq, ORC_NUM_LL, 15, dy->ll_len);
+    orc_huff_lengths(pl->d_freq, ORC_NUM_D, 15, dy->d_len);
+    for (dy->hlit = ORC_NUM_LL; dy->hlit > 257 && dy->ll_len[dy->hlit - 1] == 0; dy->hlit--) {}
+    for (dy->hdist = ORC_NUM_D; dy->hdist > 1 && dy->d_len[dy->hdist - 1] == 0; dy->hdist--) {}
+    memcpy(seq, dy->ll_len, (size_t)dy->hlit);
+    memcpy(seq + dy->hlit, dy->d_len, (size_t)dy->hdist);
+    dy->nitems = orc_rle_lengths(seq, dy->hlit + dy->hdist, dy->items);
+    for (i = 0; i < dy->nitems; i++) pl->cl_freq[dy->items[i].sym]++;
+    orc_huff_lengths(pl->cl_freq, ORC_NUM_CL, 7, dy->cl_len);
+    for (dy->hclen = 19; dy->hclen > 4 && dy->cl_len[orc_cl_order[dy->hclen - 1]] == 0; dy->hclen--) {}
+    orc_canonical_codes(dy->ll_len, ORC_NUM_LL, dy->ll_code);
+    orc_canonical_codes(dy->d_len, ORC_NUM_D, dy->d_code);
+    orc_canonical_codes(dy->cl_len, ORC_NUM_CL, dy->cl_code);
 
     /* exact costs (README.md:16,19: "calculate the compression ratio for each case") */
-    dyn_bits = 3 + 5 + 5 + 4 + 3 * dy.hclen + extra_bits;
-    for (s = 0; s < ORC_NUM_CL; s++) dyn_bits += (int64_t)cl_freq[s] * dy.cl_len[s];
-    dyn_bits += 2 * (int64_t)cl_freq[16] + 3 * (int64_t)cl_freq[17] + 7 * (int64_t)cl_freq[18];
-    for (s = 0; s < ORC_NUM_LL; s++) dyn_bits += (int64_t)ll_freq[s] * dy.ll_len[s];
-    for (s = 0; s < ORC_NUM_D; s++) dyn_bits += (int64_t)d_freq[s] * dy.d_len[s];
-    fixed_bits = 3 + extra_bits;
-    for (s = 0; s < ORC_NUM_LL; s++) fixed_bits += (int64_t)ll_freq[s] * orc_fixed_ll_len(s);
-    for (s = 0; s < ORC_NUM_D; s++) fixed_bits += (int64_t)d_freq[s] * 5;
+    pl->dyn_bits = 3 + 5 + 5 + 4 + 3 * dy->hclen + pl->extra_bits;
+    for (s = 0; s < ORC_NUM_CL; s++) pl->dyn_bits += (int64_t)pl->cl_freq[s] * dy->cl_len[s];
+    pl->dyn_bits += 2 * (int64_t)pl->cl_freq[16] + 3 * (int64_t)pl->cl_freq[17] + 7 * (int64_t)pl->cl_freq[18];
+    for (s = 0; s < ORC_NUM_LL; s++) pl->dyn_bits += (int64_t)pl->ll_freq[s] * dy->ll_len[s];
+    for (s = 0; s < ORC_NUM_D; s++) pl->dyn_bits += (int64_t)pl->d_freq[s] * dy->d_len[s];
+    pl->fixed_bits = 3 + pl->extra_bits;
+    for (s = 0; s < ORC_NUM_LL; s++) pl->fixed_bits += (int64_t)pl->ll_freq[s] * orc_fixed_ll_len(s);
+    for (s = 0; s < ORC_NUM_D; s++) pl->fixed_bits += (int64_t)pl->d_freq[s] * 5;
     nstored = (n + 65534) / 65535;
     if (nstored < 1) nstored = 1;
-    stored_bits = 8 * (n + 5 * nstored); /* a segment always starts byte aligned */
+    /* a segment always starts byte aligned; a stored block inside a split segment is costed the same way (its
+     * 3 header bits plus the padding count as one byte: the decision's yardstick, the emitted size is exact) */
+    pl->stored_bits = 8 * (n + 5 * nstored);
 
-    if (prm->block_mode == 1) btype = 0;
-    else if (prm->block_mode == 2) btype = 1;
-    else if (prm->block_mode == 3) btype = 2;
-    else if (stored_bits <= fixed_bits && stored_bits <= dyn_bits) btype = 0;
-    else if (fixed_bits <= dyn_bits) btype = 1;
-    else btype = 2;
+    if (block_mode == 1) pl->btype = 0;
+    else if (block_mode == 2) pl->btype = 1;
+    else if (block_mode == 3) pl->btype = 2;
+    else if (pl->stored_bits <= pl->fixed_bits && pl->stored_bits <= pl->dyn_bits) pl->btype = 0;
+    else if (pl->fixed_bits <= pl->dyn_bits) pl->btype = 1;
+    else pl->btype = 2;
+}
 
+/* The block itself (not final: the sync marker that follows a segment carries BFINAL). */
+static void orc_emit_block(orc_bw *bw, const orc_plan *pl, const uint8_t *raw, long n, const uint32_t *tokens, long ntok)
+{
+    const orc_dyn *dy = &pl->dy;
+    const int btype = pl->btype;
+    long k;
+    int s, eb, ev, i;
     if (btype == 0) {
         long off = 0;
         do {
@@ -537,8 +554,8 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
             off += len;
         } while (off < n);
     } else {
-        const uint8_t *ll_len = dy.ll_len, *d_len = dy.d_len;
-        const uint16_t *ll_code = dy.ll_code, *d_code = dy.d_code;
+        const uint8_t *ll_len = dy->ll_len, *d_len = dy->d_len;
+        const uint16_t *ll_code = dy->ll_code, *d_code = dy->d_code;
         uint8_t fl_len[288], fd_len[32];
         uint16_t fl_code[288], fd_code[32];
         bw_put(bw, 0, 1);
@@ -552,16 +569,16 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
             orc_canonical_codes(fd_len, 32, fd_code);
             ll_len = fl_len; d_len = fd_len; ll_code = fl_code; d_code = fd_code;
         } else {
-            bw_put(bw, (uint32_t)(dy.hlit - 257), 5);
-            bw_put(bw, (uint32_t)(dy.hdist - 1), 5);
-            bw_put(bw, (uint32_t)(dy.hclen - 4), 4);
-            for (i = 0; i < dy.hclen; i++) bw_put(bw, dy.cl_len[orc_cl_order[i]], 3);
-            for (i = 0; i < dy.nitems; i++) {
-                int cs = dy.items[i].sym;
-                bw_put(bw, dy.cl_code[cs], dy.cl_len[cs]);
-                if (cs == 16) bw_put(bw, dy.items[i].extra, 2);
-                else if (cs == 17) bw_put(bw, dy.items[i].extra, 3);
-                else if (cs == 18) bw_put(bw, dy.items[i].extra, 7);
+            bw_put(bw, (uint32_t)(dy->hlit - 257), 5);
+            bw_put(bw, (uint32_t)(dy->hdist - 1), 5);
+            bw_put(bw, (uint32_t)(dy->hclen - 4), 4);
+            for (i = 0; i < dy->hclen; i++) bw_put(bw, dy->cl_len[orc_cl_order[i]], 3);
+            for (i = 0; i < dy->nitems; i++) {
+                int cs = dy->items[i].sym;
+                bw_put(bw, dy->cl_code[cs], dy->cl_len[cs]);
+                if (cs == 16) bw_put(bw, dy->items[i].extra, 2);
+                else if (cs == 17) bw_put(bw, dy->items[i].extra, 3);
+                else if (cs == 18) bw_put(bw, dy->items[i].extra, 7);
             }
         }
         for (k = 0; k < ntok; k++) {
@@ -579,6 +596,97 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
         }
         bw_put(bw, ll_code[256], ll_len[256]);
     }
+}
+
+/* cost split of a planned block (what the reference's per-token record estimates, src/deflate_compress.c:291-309) */
+static void plan_split_costs(const orc_plan *pl, int64_t *tree, int64_t *ll, int64_t *d)
+{
+    int s;
+    *tree = 0; *d = 0;
+    if (pl->btype == 0) {
+        *ll = pl->stored_bits - 3;
+    } else {
+        int64_t llb = pl->extra_bits - pl->d_extra_bits, db = pl->d_extra_bits;
+        for (s = 0; s < ORC_NUM_LL; s++) llb += (int64_t)pl->ll_freq[s] * (pl->btype == 2 ? pl->dy.ll_len[s] : orc_fixed_ll_len(s));
+        for (s = 0; s < ORC_NUM_D; s++) db += (int64_t)pl->d_freq[s] * (pl->btype == 2 ? pl->dy.d_len[s] : 5);
+        *ll = llb;
+        *d = db;
+        *tree = plan_bits(pl) - 3 - llb - db;
+    }
+}
+
+/*
+ * Adaptive block splitting (block_mode 4; the reference's stated aim, README.md:15-20 "how to divide the data up into
+ * chunks, each able to have its own Huffman coding", which it approaches with the running cost of an adaptive tree,
+ * src/aht.c:239-277 -- never wired to a decision).  Decided here from exact block costs: the segment's tokens are cut
+ * where they cross multiples of ORC_SUB_BYTES input bytes (sub-block j = the tokens that START in
+ * [j * ORC_SUB_BYTES, (j + 1) * ORC_SUB_BYTES)); a range of sub-blocks is bisected when its two halves, each with its own
+ * cheapest block, cost strictly fewer bits than the range as one block; the halves are then looked at the same way.
+ * The token stream is untouched.
+ */
+static void orc_split_range(orc_bw *bw, const uint8_t *raw, const uint32_t *tokens, const long *tok_start, const long *pos_start,
+                            int a, int b, const orc_plan *whole, orc_seg_stats *st)
+{
+    orc_plan *L = NULL, *R = NULL;
+    if (b - a >= 2) {
+        const int mid = (a + b) / 2;
+        L = (orc_plan *)malloc(sizeof(orc_plan));
+        R = (orc_plan *)malloc(sizeof(orc_plan));
+        orc_plan_block(L, pos_start[mid] - pos_start[a], tokens + tok_start[a], tok_start[mid] - tok_start[a], 0);
+        orc_plan_block(R, pos_start[b] - pos_start[mid], tokens + tok_start[mid], tok_start[b] - tok_start[mid], 0);
+        if (plan_bits(L) + plan_bits(R) < plan_bits(whole)) {
+            orc_split_range(bw, raw, tokens, tok_start, pos_start, a, mid, L, st);
+            orc_split_range(bw, raw, tokens, tok_start, pos_start, mid, b, R, st);
+            free(L); free(R);
+            return;
+        }
+        free(L); free(R);
+    }
+    orc_emit_block(bw, whole, raw + pos_start[a], pos_start[b] - pos_start[a], tokens + tok_start[a], tok_start[b] - tok_start[a]);
+    if (st) {
+        int64_t t, l, d;
+        plan_split_costs(whole, &t, &l, &d);
+        if (st->nblocks == 0) st->btype = whole->btype;
+        st->nblocks++;
+        st->block_bits += plan_bits(whole);
+        st->tree_bits += t; st->ll_bits += l; st->d_bits += d;
+    }
+}
+
+/* Emit one segment: its block(s) then the byte-aligning empty stored block. */
+static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint32_t *tokens,
+                             long ntok, const orc_params *prm, int final_seg, orc_seg_stats *st)
+{
+    orc_plan *pl = (orc_plan *)malloc(sizeof(orc_plan));
+    long start_pos = bw->pos;
+    orc_plan_block(pl, n, tokens, ntok, prm->block_mode == 4 ? 0 : prm->block_mode);
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        st->ntokens = (int32_t)ntok;
+        st->stored_bits = pl->stored_bits;
+        st->fixed_bits = pl->fixed_bits;
+        st->dynamic_bits = pl->dyn_bits;
+    }
+    if (prm->block_mode == 4 && n > ORC_SUB_BYTES) {
+        long tok_start[ORC_SUB_MAX + 1], pos_start[ORC_SUB_MAX + 1], k, pos = 0;
+        const int nsub = (int)((n + ORC_SUB_BYTES - 1) / ORC_SUB_BYTES);
+        int j = 0;
+        for (k = 0; k < ntok; k++) {
+            while (j <= pos / ORC_SUB_BYTES) { tok_start[j] = k; pos_start[j] = pos; j++; } /* (a token is shorter than a sub-block) */
+            pos += ORC_TOK_DIST(tokens[k]) ? (long)ORC_TOK_LEN(tokens[k]) : 1;
+        }
+        for (; j <= nsub; j++) { tok_start[j] = ntok; pos_start[j] = n; }
+        tok_start[nsub] = ntok; pos_start[nsub] = n;
+        orc_split_range(bw, raw, tokens, tok_start, pos_start, 0, nsub, pl, st);
+    } else {
+        orc_emit_block(bw, pl, raw, n, tokens, ntok);
+        if (st) {
+            st->btype = pl->btype;
+            st->nblocks = 1;
+            st->block_bits = plan_bits(pl);
+            plan_split_costs(pl, &st->tree_bits, &st->ll_bits, &st->d_bits);
+        }
+    }
     /* sync marker: empty stored block, byte aligns the segment
      * (RFC 1951 3.2.4, docs/rfc1951.txt:576-587) */
     bw_put(bw, final_seg ? 1u : 0u, 1);
@@ -586,29 +694,8 @@ static void orc_emit_segment(orc_bw *bw, const uint8_t *raw, long n, const uint3
     bw_align(bw);
     bw_put(bw, 0x0000, 16);
     bw_put(bw, 0xFFFF, 16);
-
-    if (st) {
-        st->btype = btype;
-        st->ntokens = (int32_t)ntok;
-        st->stored_bits = stored_bits;
-        st->fixed_bits = fixed_bits;
-        st->dynamic_bits = dyn_bits;
-        st->block_bits = btype == 0 ? stored_bits : btype == 1 ? fixed_bits : dyn_bits;
-        st->out_bytes = bw->pos - start_pos;
-        /* cost split (what the reference's per-token record estimates, src/deflate_compress.c:291-309) */
-        st->tree_bits = 0;
-        st->d_bits = 0;
-        if (btype == 0) {
-            st->ll_bits = stored_bits - 3;
-        } else {
-            int64_t llb = extra_bits - d_extra_bits, db = d_extra_bits;
-            for (s = 0; s < ORC_NUM_LL; s++) llb += (int64_t)ll_freq[s] * (btype == 2 ? dy.ll_len[s] : orc_fixed_ll_len(s));
-            for (s = 0; s < ORC_NUM_D; s++) db += (int64_t)d_freq[s] * (btype == 2 ? dy.d_len[s] : 5);
-            st->ll_bits = llb;
-            st->d_bits = db;
-            st->tree_bits = st->block_bits - 3 - llb - db;
-        }
-    }
+    if (st) st->out_bytes = bw->pos - start_pos;
+    free(pl);
 }
 
 long orc_num_segments(long n, const orc_params *prm)
@@ -619,7 +706,7 @@ long orc_num_segments(long n, const orc_params *prm)
 long orc_bound(long n, const orc_params *prm)
 {
     long nseg = orc_num_segments(n, prm);
-    long per = 5 * ((prm->seg_bytes + 65534) / 65535) + 5 + 8;
+    long per = 5 * ((prm->seg_bytes + 65534) / 65535) + 5 + 8 + (prm->block_mode == 4 ? 6 * ORC_SUB_MAX : 0);
     if (prm->block_mode >= 2) return 2 * n + nseg * 640 + 64; /* forced fixed/dynamic may expand */
     return n + nseg * per + 64;
 }

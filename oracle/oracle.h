@@ -45,13 +45,18 @@ typedef struct orc_params {
     int32_t seg_bytes;   /* independent segment size; parse restarts, one block + sync marker each */
     int32_t chain_limit; /* 0 = unlimited (reference behaviour); K = newest K entries of the 4-byte bucket, then the nearest 3-byte match */
     int32_t use_dict;    /* 1: a segment may match into the <=window bytes before it */
-    int32_t block_mode;  /* 0 = choose cheapest of stored/fixed/dynamic; 1/2/3 = force stored/fixed/dynamic */
+    int32_t block_mode;  /* 0 = choose cheapest of stored/fixed/dynamic; 1/2/3 = force stored/fixed/dynamic;
+                          * 4 = cheapest, and a segment may be split into up to ORC_SUB_MAX blocks (adaptive block splitting) */
 } orc_params;
 
+#define ORC_SUB_BYTES 4096 /* block_mode 4: a segment is cut where its tokens cross multiples of this many input bytes */
+#define ORC_SUB_MAX 8      /* 32768 / ORC_SUB_BYTES */
+
 typedef struct orc_seg_stats {
-    int32_t btype;       /* 0 stored, 1 fixed, 2 dynamic */
+    int32_t btype;       /* 0 stored, 1 fixed, 2 dynamic (block_mode 4: of the segment's first block) */
     int32_t ntokens;
-    int64_t block_bits;  /* bits of the block(s) incl. 3-bit header, excl. sync marker */
+    int64_t block_bits;  /* bits of the block(s) incl. 3-bit header(s), excl. sync marker (a stored block inside a split
+                          * segment counts 8 * (bytes + 5)) */
     int64_t out_bytes;   /* bytes of the segment incl. sync marker */
     int64_t stored_bits, fixed_bits, dynamic_bits;
     /* the chosen block's cost split the way struct compress_stats reports it (src/include/deflate_ext.h:19-31):
@@ -59,6 +64,7 @@ typedef struct orc_seg_stats {
     int64_t tree_bits; /* code description: HLIT/HDIST/HCLEN, code-length code, run-length coded lengths (0 unless dynamic) */
     int64_t ll_bits;   /* lit/len symbols + length extra bits (stored: everything but the 3 header bits) */
     int64_t d_bits;    /* distance symbols + distance extra bits */
+    int64_t nblocks;   /* blocks of the segment (1 unless block_mode 4 split it); tree + ll + d + 3 * nblocks == block_bits */
 } orc_seg_stats;
 
 void orc_default_params(orc_params *p);

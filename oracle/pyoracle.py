@@ -43,6 +43,7 @@ class OrcSegStats(C.Structure):
         ("tree_bits", C.c_int64),
         ("ll_bits", C.c_int64),
         ("d_bits", C.c_int64),
+        ("nblocks", C.c_int64),
     ]
 
 

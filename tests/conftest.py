@@ -54,3 +54,21 @@ def golden_cases():
         seed, off, n = (int(v) for v in z[f"{name}__spec"])
         out.append((name, kind, seed, off, n, z[f"{name}__tokens"], z[f"{name}__last"], z[f"{name}__sha"]))
     return out
+
+
+def striped_input(n: int, seed: int = 11) -> np.ndarray:
+    """Data whose statistics change every few KiB (text / random bytes / a numeric table, stripes of 2-12 KiB): the
+    case adaptive block splitting (block_mode 4) exists for."""
+    rng = np.random.default_rng(seed)
+    parts, tot, i = [], 0, 0
+    while tot < n:
+        m = int(rng.integers(2000, 12000))
+        if i % 3 == 0:
+            parts.append(make_input("markov", seed + i, 0, m))
+        elif i % 3 == 1:
+            parts.append(rng.integers(0, 256, m, dtype=np.uint8))
+        else:
+            parts.append(np.frombuffer((b"%d,%d;" % (i, i * 7)) * (m // 6 + 1), dtype=np.uint8)[:m].copy())
+        tot += m
+        i += 1
+    return np.concatenate(parts)[:n]

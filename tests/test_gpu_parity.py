@@ -847,3 +847,69 @@ def test_gpu_inflate_corrupt_streams_fail_cleanly(D, seed):
             comp.decompress(z, bad_off, data.size)
     assert comp.decompress(z, off, data.size) == data.tobytes()  # the context survives all of it
     comp.close()
+
+
+# ---- adaptive block splitting (block_mode 4) ----
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed,n", [("markov", 2, 150001), ("log", 3, 100000), ("png", 6, 100000), ("random", 4, 70000),
+                                         ("zeros", 0, 70000), ("striped", 11, 300000), ("striped", 12, 4097), ("markov", 1, 4096),
+                                         ("markov", 1, 8200), ("striped", 13, 40000), ("striped", 14, 32768 * 3 + 5)])
+def test_split_stream_equals_oracle(D, O, kind, seed, n):
+    """block_mode 4: same tokens as the oracle, the emitted stream == the oracle's byte for byte (block boundaries,
+    types, headers, the byte alignment of a stored block inside a segment), and it inflates everywhere."""
+    from conftest import striped_input
+    data = striped_input(n, seed) if kind == "striped" else make_input(kind, seed, 0, n)
+    check_stream(D, O, data, block_mode=4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prm", [dict(seg_bytes=16384), dict(seg_bytes=5000), dict(window=4096), dict(use_dict=0), dict(chain_limit=8)], ids=str)
+def test_split_with_other_geometries(D, O, prm):
+    from conftest import striped_input
+    check_stream(D, O, striped_input(120000, 21), block_mode=4, **prm)
+
+
+@pytest.mark.gpu
+def test_split_seg_info_matches_oracle_stats(D, O):
+    """Per segment: block count, summed block bits and the cost split == orc_seg_stats; never more bits than unsplit."""
+    from conftest import striped_input
+    data = striped_input(1 << 18, 11)
+    comp = D.Compressor(block_mode=4)
+    comp.keep_tokens(True)
+    z = comp.compress(data)
+    _, st4 = O.deflate_body(data, 0, data.size, O.params(block_mode=4))
+    _, st0 = O.deflate_body(data, 0, data.size, O.params(block_mode=0))
+    assert comp.num_segments() == len(st4)
+    split_any = False
+    for s, (a, b) in enumerate(zip(st4, st0)):
+        i = comp.seg_info(s)
+        assert (i.nblocks, i.btype, i.block_bits, i.out_bytes) == (a.nblocks, a.btype, a.block_bits, a.out_bytes), s
+        assert (i.tree_bits, i.ll_bits, i.d_bits) == (a.tree_bits, a.ll_bits, a.d_bits), s
+        assert i.tree_bits + i.ll_bits + i.d_bits + 3 * i.nblocks == i.block_bits <= b.block_bits
+        split_any |= i.nblocks > 1
+    assert split_any
+    assert len(z) < len(zlib.compress(data.tobytes(), 6))
+    comp.close()
+
+
+@pytest.mark.gpu
+def test_split_gpu_inflate_and_sharded(D, O):
+    """A split stream through the GPU inflate (several blocks per segment, stored blocks among them), and block_mode 4
+    on a shard with history == the oracle's body for that range."""
+    import torch
+    from conftest import striped_input
+    data = striped_input(400000, 31)
+    comp = D.Compressor(block_mode=4)
+    z = comp.compress(data)
+    assert comp.decompress(z, comp.seg_index(), data.size) == data.tobytes()
+    lo, hi = 3 * 32768, 9 * 32768
+    dev = torch.device("cuda:0")
+    d_in = torch.from_numpy(data).to(dev)
+    cap = comp.bound(hi - lo)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    out_len, adler = comp.deflate_device(d_in.data_ptr() + lo, hi - lo, 32768, False, d_out.data_ptr(), cap)
+    ob, _ = O.deflate_body(data, lo, hi, O.params(block_mode=4), is_final=False)
+    assert d_out[:out_len].cpu().numpy().tobytes() == ob
+    assert adler == O.adler32(data[lo:hi])
+    comp.close()

@@ -253,3 +253,42 @@ def test_crc32_matches_zlib(O):
 
     for data in (b"", b"IEND", b"123456789", bytes(range(256)) * 9):
         assert O.crc32(data) == (zlib.crc32(data) & 0xFFFFFFFF)
+
+
+# ---- adaptive block splitting (block_mode 4; SURVEY.md section 8(f) N2, README.md:15-20) ----
+
+@pytest.mark.parametrize("kind,seed,n", [("markov", 2, 150001), ("log", 3, 100000), ("png", 6, 100000), ("random", 4, 70000),
+                                         ("zeros", 0, 70000), ("striped", 11, 200000), ("striped", 12, 4097), ("markov", 1, 4096),
+                                         ("markov", 1, 8200), ("striped", 13, 40000)])
+def test_split_roundtrip_never_worse_same_tokens(O, kind, seed, n):
+    """A split stream inflates (zlib and the oracle's inflate), holds the SAME tokens, and no segment takes more bits
+    than it does as one block; tree + ll + d + 3 per block == block_bits."""
+    from conftest import striped_input
+    data = striped_input(n, seed) if kind == "striped" else make_input(kind, seed, 0, n)
+    z4 = O.zlib_compress(data, O.params(block_mode=4))
+    assert zlib.decompress(z4) == data.tobytes()
+    assert O.zlib_decompress(z4, n) == data.tobytes()
+    _, st0 = O.deflate_body(data, 0, n, O.params(block_mode=0))
+    _, st4 = O.deflate_body(data, 0, n, O.params(block_mode=4))
+    assert len(st0) == len(st4)
+    for a, b in zip(st0, st4):
+        assert a.ntokens == b.ntokens and a.nblocks == 1 and 1 <= b.nblocks <= 8
+        assert b.block_bits <= a.block_bits
+        assert (b.nblocks == 1) == (b.block_bits == a.block_bits)  # a split is taken only when it saves bits
+        assert b.tree_bits + b.ll_bits + b.d_bits + 3 * b.nblocks == b.block_bits
+        assert (a.stored_bits, a.fixed_bits, a.dynamic_bits) == (b.stored_bits, b.fixed_bits, b.dynamic_bits)
+    assert len(z4) <= len(O.zlib_compress(data, O.params(block_mode=0)))
+
+
+def test_split_pays_on_striped_data_and_beats_zlib6(O):
+    """Where the statistics change inside a segment the split stream is clearly smaller -- smaller than zlib level 6,
+    which the unsplit stream (one block per 32 KiB) is not."""
+    from conftest import striped_input
+    data = striped_input(1 << 18, 11)
+    z0 = O.zlib_compress(data, O.params(block_mode=0))
+    z4 = O.zlib_compress(data, O.params(block_mode=4))
+    z6 = zlib.compress(data.tobytes(), 6)
+    assert len(z4) < 0.98 * len(z0)
+    assert len(z4) < len(z6) < len(z0)
+    _, st4 = O.deflate_body(data, 0, data.size, O.params(block_mode=4))
+    assert max(s.nblocks for s in st4) >= 4

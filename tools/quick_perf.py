@@ -29,7 +29,7 @@ def run(name, data, reps=3, **prm):
             print("   !! sort fallbacks:", fb)
     ms, k, ph = best
     nseg = (data.size + 32767) // 32768
-    print("   per-segment k_match cycles: " + " ".join(f"{a}={b/nseg:.0f}" for a, b in ph.items() if a != "d11"))
+    print("   per-segment k_match cycles: " + " ".join(f"{a}={b/nseg:.0f}" for a, b in ph.items() if b))
     print(f"{name:28s} n={data.size>>20:5d} MiB out={out_len/data.size:.4f} {ms:9.2f} ms {data.size/ms/1e6:8.2f} GB/s  " +
           " ".join(f"{a}={b:.2f}" for a, b in k.items()), flush=True)
     comp.close()
