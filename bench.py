@@ -329,6 +329,71 @@ def other_workloads(D, comp, dev, rank: int, world: int, stream: int, dist, peak
     return res
 
 
+def striped_corpus(n: int, seed: int = 7) -> np.ndarray:
+    """Data whose statistics change every 2-12 KiB (text, random bytes, a numeric table in turn): what adaptive block
+    splitting is for.  Cut from three long buffers, so generating it costs next to nothing."""
+    from deflate_compression_b200 import synth
+
+    rng = np.random.default_rng(seed)
+    src = [synth.markov(n // 2 + 16384, 9), synth.random_bytes(n // 2 + 16384, 9),
+           np.frombuffer(b"".join(b"%d,%d;" % (i, i * 7) for i in range(n // 20)), dtype=np.uint8)]
+    pos = [0, 0, 0]
+    out = np.empty(n, dtype=np.uint8)
+    o = i = 0
+    while o < n:
+        k = i % 3
+        m = min(int(rng.integers(2048, 12288)), n - o, src[k].size - pos[k])
+        if m <= 0:
+            pos[k] = 0
+            continue
+        out[o:o + m] = src[k][pos[k]:pos[k] + m]
+        pos[k] += m
+        o += m
+        i += 1
+    return out
+
+
+def block_split_report(D, dev, local: int, d_buf, hist: int, n: int, stream: int, host_sample: np.ndarray, unsplit_ratio: float) -> dict:
+    """Adaptive block splitting (block_mode 4) beside the headline: one device-timed pass over the
+    resident benchmark text and one over 64 MiB of striped data, each with the device round trip, and the ratios next
+    to zlib level 6 on a sample."""
+    import torch
+    import zlib
+
+    res = {}
+    comp4 = D.Compressor(device=local, block_mode=4)
+    comp4.enable_timing(True)
+    comp0 = D.Compressor(device=local)
+
+    def one(name, d_in, h, nn, sample):
+        cap = comp4.bound(nn)
+        d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        ms, out_len, adler, k = device_pass(comp4, d_in.data_ptr() + h, nn, h, True, d_out, cap, stream)
+        d_off = torch.from_numpy(comp4.seg_index().astype(np.int64)).to(dev)
+        d_back = torch.empty(h + nn, dtype=torch.uint8, device=dev)
+        d_back[:h].copy_(d_in[:h])
+        a2 = comp4.inflate_device(d_out.data_ptr(), out_len, d_off.data_ptr(), (nn + 32767) // 32768, d_back.data_ptr() + h, nn, h, stream)
+        ok = bool(a2 == adler) and bool(torch.equal(d_back[h:], d_in[h:h + nn]))
+        _, out0, _, _ = device_pass(comp0, d_in.data_ptr() + h, nn, h, True, d_out, cap, stream, reps=1)
+        res[name] = {"value": nn / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ms, "input_bytes": int(nn), "ratio_split": nn / out_len,
+                     "ratio_one_block_per_segment": nn / out0, "bytes_saved_pct": 100.0 * (out0 - out_len) / out0,
+                     "ratio_zlib6_on_sample": sample.size / len(zlib.compress(sample.tobytes(), 6)), "sample_bytes": int(sample.size),
+                     "kernel_ms": {a: round(b, 3) for a, b in k.items() if b}, "roundtrip_ok": ok}
+        del d_out, d_back, d_off
+
+    one("text", d_buf, hist, n, host_sample)
+    striped = striped_corpus(64 << 20)
+    d_s = torch.from_numpy(striped).to(dev)
+    one("striped", d_s, 0, striped.size, striped[:16 << 20])
+    del d_s
+    comp4.close()
+    comp0.close()
+    torch.cuda.empty_cache()
+    res["what"] = ("block_mode 4: a 32 KiB segment is cut where its tokens cross multiples of 4 KiB and bisected top-down while "
+                   "two halves, each its own cheapest block by exact cost, take fewer bits than one block; same tokens")
+    return res
+
+
 def e2e_fd_throughput(D, host_bytes: np.ndarray, reps: int = 3):
     """GB/s of the reference entry point itself: deflate_compress(fd_in, fd_out, -1, 32768, 0) over memfds."""
     fi, fo = os.memfd_create("dfl_in"), os.memfd_create("dfl_out")
@@ -600,7 +665,10 @@ def run_gpu(args) -> None:
     del d_outs, d_out, gather_bufs, timed_out
     torch.cuda.empty_cache()
     others = None
+    split = None
     if not args.no_other_workloads:
+        if rank == 0:
+            split = block_split_report(D, dev, local, d_buf, hist, n, stream, host[hist:hist + CPU_SAMPLE], n_total / out_total)
         others = other_workloads(D, comp, dev, rank, world, stream, dist, peak)
 
     if rank == 0:
@@ -637,6 +705,8 @@ def run_gpu(args) -> None:
                            "roundtrip_ok": inf_bad == 0.0}
         if others is not None:
             line["other_workloads"] = others
+        if split is not None:
+            line["block_split"] = split
         if world > 1:
             line["compress_only_value"] = n_total * args.steps / (ms_nogather * 1e-3) / 1e9
         # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's single-threaded compressor ----

@@ -51,6 +51,14 @@ static int env_device(void)
     return e && *e ? atoi(e) : 0;
 }
 
+/* Nor have they a knob for the blocks: DFL_B200_SPLIT=1 turns adaptive block splitting on (block_mode 4: a 32 KiB
+ * segment becomes up to 8 blocks where that saves bits -- the reference's stated aim, README.md:15-20). */
+static int env_block_mode(void)
+{
+    const char *e = getenv("DFL_B200_SPLIT");
+    return e && *e && atoi(e) ? 4 : 0;
+}
+
 static void parked_release(void)
 {
     pthread_mutex_lock(&parked_mu);
@@ -83,9 +91,13 @@ void deflate_compr_init(deflate_compr_t *com, int fd_in, int fd_out, int fd_stat
         parked_ctx = NULL;
     }
     pthread_mutex_unlock(&parked_mu);
-    if (com->ctx) return;
     dfl_b200_default_params(&prm);
     prm.window = sw;
+    prm.block_mode = env_block_mode();
+    if (com->ctx) { /* (the parked context may have been used with the other block mode) */
+        com->err = map_err(dfl_b200_set_params(com->ctx, &prm));
+        return;
+    }
     com->err = map_err(dfl_b200_create(&com->ctx, env_device(), &prm));
 }
 

@@ -48,8 +48,9 @@ int main(int argc, char *argv[])
         if (!strcmp(argv[i], "-d")) decompress = 1;
         else if (!strcmp(argv[i], "-w") && i + 1 < argc) window = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-s") && i + 1 < argc) stats = argv[++i];
+        else if (!strcmp(argv[i], "-b")) setenv("DFL_B200_SPLIT", "1", 1); /* adaptive block splitting */
         else if (argv[i][0] == '-' && argv[i][1]) {
-            fprintf(stderr, "USAGE: %s [-d] [-w window] [-s stats_file] [infile [outfile]]\n", argv[0]);
+            fprintf(stderr, "USAGE: %s [-d] [-b] [-w window] [-s stats_file] [infile [outfile]]\n", argv[0]);
             return 2;
         } else if (nfiles < 2) files[nfiles++] = argv[i];
     }

@@ -158,10 +158,11 @@ struct HuffPlan {
 /*
  * Code construction + exact block costs + choice for ONE block whose lit/len and distance counts (EOB included) are in
  * S.ll_freq / S.d_freq, by one warp.  Leaves the chosen block's packed header in S.hdr and, for a dynamic block, its
- * codes in S.ll_code / S.d_code.  Twin of orc_plan_block (oracle/deflate_oracle.c); what the reference accounts per
+ * codes in S.ll_code / S.d_code (unless cost_only).  Twin of orc_plan_block (oracle/deflate_oracle.c); what the reference accounts per
  * token in h_tree_d_lens / h_tree_builder_* (src/h_tree.c:75-148, :242-302) is done once per block here.
  */
-__device__ HuffPlan huff_plan(HuffSmem &S, const int lane, const unsigned long long extra, const long long nbytes, const int block_mode)
+__device__ HuffPlan huff_plan(HuffSmem &S, const int lane, const unsigned long long extra, const long long nbytes, const int block_mode,
+                              const bool cost_only = false)
 {
     S.cl_freq[lane] = 0;
     for (int i = lane; i < HDR_WORDS; i += 32) S.hdr[i] = 0;
@@ -259,7 +260,9 @@ __device__ HuffPlan huff_plan(HuffSmem &S, const int lane, const unsigned long l
         P.block_bits = btype == 0 ? stored : btype == 1 ? fix : dyn;
 
         BitW bw{S.hdr, 0};
-        if (btype == 2) {
+        if (cost_only) {
+            /* only the decision is wanted (k_huff_split weighing a split): no codes, no header */
+        } else if (btype == 2) {
             canonical_codes_lane0(S.ll_len, NLL, S.ll_code);
             canonical_codes_lane0(S.d_len, ND, S.d_code);
             canonical_codes_lane0(S.cl_len, NCL, S.cl_code);
@@ -425,7 +428,7 @@ k_huff_split(long long n, long long seg0, int nseg, dfl_params prm, const uint32
     __syncwarp();
 
     /* a block over sub-blocks [a, b): counts summed into the plan's tables, one EOB */
-    auto plan_range = [&](int a, int b) -> HuffPlan {
+    auto plan_range = [&](int a, int b, bool cost_only) -> HuffPlan {
         for (int s = lane; s < LLS; s += 32) {
             uint32_t f = s == 256 ? 1u : 0u;
             for (int j = a; j < b; j++) f += S.sub_ll[j][s];
@@ -436,28 +439,33 @@ k_huff_split(long long n, long long seg0, int nseg, dfl_params prm, const uint32
         S.H.d_freq[lane] = lane < ND ? fd : 0u;
         ex = __reduce_add_sync(FULL, ex);
         __syncwarp();
-        return huff_plan(S.H, lane, ex, (long long)S.pos_start[b] - (long long)S.pos_start[a], prm.block_mode == 4 ? 0 : prm.block_mode);
+        return huff_plan(S.H, lane, ex, (long long)S.pos_start[b] - (long long)S.pos_start[a], prm.block_mode == 4 ? 0 : prm.block_mode, cost_only);
     };
 
-    /* ---- top-down bisection (explicit stack: ranges still to be looked at, leftmost on top) ---- */
+    /* ---- top-down bisection (explicit stack: ranges still to be looked at, leftmost on top; a range that came out of
+     * a split brings its cost along) ---- */
     int st_a[4], st_b[4], sp = 0;
-    st_a[0] = 0; st_b[0] = nsub; sp = 1;
+    unsigned long long st_c[4];
+    st_a[0] = 0; st_b[0] = nsub; st_c[0] = 0; sp = 1;
     uint32_t nblk = 0, tree_sum = 0, d_sum = 0, first_type = 0;
     unsigned long long bits_sum = 0, run_bits = 0; /* costs as planned; exact bits of the segment's stream so far */
     while (sp > 0) {
         sp--;
         const int a = st_a[sp], b = st_b[sp];
+        HuffPlan P;
+        bool have = false; /* the plan's tables are this range's, in full */
         if (b - a >= 2) {
             const int mid = (a + b) / 2;
-            const HuffPlan L = plan_range(a, mid), R = plan_range(mid, b);
-            const HuffPlan W = plan_range(a, b);
-            if (L.block_bits + R.block_bits < W.block_bits) {
-                st_a[sp] = mid; st_b[sp] = b; sp++;
-                st_a[sp] = a; st_b[sp] = mid; sp++;
+            const HuffPlan L = plan_range(a, mid, true), R = plan_range(mid, b, true);
+            unsigned long long w = st_c[sp];
+            if (!w) { P = plan_range(a, b, false); w = P.block_bits; have = true; } /* the whole segment: planned in full, it is the likely outcome */
+            if (L.block_bits + R.block_bits < w) {
+                st_a[sp] = mid; st_b[sp] = b; st_c[sp] = R.block_bits; sp++;
+                st_a[sp] = a; st_b[sp] = mid; st_c[sp] = L.block_bits; sp++;
                 continue;
             }
         }
-        const HuffPlan P = plan_range(a, b); /* (for a range just declined this repeats W: the plan's tables are the last one's) */
+        if (!have) P = plan_range(a, b, false); /* the block: codes, header */
         const size_t gb = (size_t)sl * DFL_SUB_MAX + nblk;
         const uint32_t nb = S.pos_start[b] - S.pos_start[a];
         if (lane == 0) {

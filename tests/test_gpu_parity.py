@@ -913,3 +913,35 @@ def test_split_gpu_inflate_and_sharded(D, O):
     assert d_out[:out_len].cpu().numpy().tobytes() == ob
     assert adler == O.adler32(data[lo:hi])
     comp.close()
+
+
+@pytest.mark.gpu
+def test_split_through_the_reference_entry_point(D, O, tmp_path, monkeypatch):
+    """DFL_B200_SPLIT=1 switches deflate_compress(fd_in, fd_out, fd_stats, sw, ops) to block_mode 4, with and without
+    a record stream; the next call without it is back to one block per segment (the context is parked in between)."""
+    from conftest import striped_input
+    data = striped_input(300000, 41)
+    src = tmp_path / "in"
+    src.write_bytes(data.tobytes())
+
+    def run(with_stats):
+        dst, st = tmp_path / "out.z", tmp_path / "stats"
+        fi = os.open(src, os.O_RDONLY)
+        fo = os.open(dst, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        fs = os.open(st, os.O_WRONLY | os.O_CREAT | os.O_TRUNC) if with_stats else -1
+        try:
+            assert D.deflate_compress(fi, fo, fs, 32768, 0) == 0
+        finally:
+            os.close(fi), os.close(fo)
+            if fs >= 0:
+                os.close(fs)
+        return dst.read_bytes()
+
+    z4 = O.zlib_compress(data, O.params(block_mode=4))
+    z0 = O.zlib_compress(data, O.params())
+    assert len(z4) < len(z0)
+    monkeypatch.setenv("DFL_B200_SPLIT", "1")
+    assert run(False) == z4
+    assert run(True) == z4
+    monkeypatch.delenv("DFL_B200_SPLIT")
+    assert run(False) == z0
