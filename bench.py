@@ -436,6 +436,10 @@ def run_gpu(args) -> None:
     if world > 1:
         import datetime
 
+        # (measured at N = 2: capping NCCL's send / recv at one channel makes the 125 MB per step the bottleneck, 28 instead of
+        # 39 GB/s; the default fan of channels costs 4 % against compress-only.  DFL_BENCH_P2P_CHANNELS overrides.)
+        if os.environ.get("DFL_BENCH_P2P_CHANNELS"):
+            os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", os.environ["DFL_BENCH_P2P_CHANNELS"])
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     D.build()
 

@@ -431,8 +431,21 @@ static int launch_chunk(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist
     /* the default geometry (the window of a segment is the segment before it): runs of consecutive segments per
      * CTA, the window's index inherited (k_match_run); anything else: one CTA per segment (k_match) */
     if (!ctx->match_mode && prm.seg_bytes == DFL_MAX_SEG && prm.window == DFL_MAX_WINDOW && prm.use_dict && !prm.chain_limit) {
-        int run_segs = ns / (4 * ctx->num_sms);
-        run_segs = run_segs < 1 ? 1 : run_segs > RUN_SEGS ? RUN_SEGS : run_segs;
+        /* Segments per run.  A run costs r segments plus one more index build (its first segment sorts its window
+         * itself: ~0.22 of a segment's time), and the runs go round the SMs in waves: take the r whose waves x run cost
+         * is least, and among the ones within 1.5 % of it the shortest (more runs: the counter evens out SMs that
+         * were placed late or drew slower data). */
+        int run_segs = 1;
+        {
+            double best = 1e30, cost[RUN_SEGS_MAX + 1];
+            for (int r = 1; r <= RUN_SEGS_MAX; r++) {
+                const int nr = (ns + r - 1) / r;
+                cost[r] = (double)((nr + ctx->num_sms - 1) / ctx->num_sms) * ((r < ns ? r : ns) + 0.22);
+                if (cost[r] < best) best = cost[r];
+            }
+            for (int r = RUN_SEGS_MAX; r >= 1; r--)
+                if (cost[r] <= 1.015 * best) run_segs = r;
+        }
         const int nruns = (ns + run_segs - 1) / run_segs;
         LAUNCH(K_MATCH, k_match_run, nruns < ctx->num_sms ? nruns : ctx->num_sms, MATCH_THREADS, sizeof(MatchSmem), st, d_in, (long long)n,
                (long long)hist_len, (long long)s0, ns, run_segs, ctx->tokcand, ctx->scratch, ctx->state);

@@ -2,9 +2,7 @@
  * (included by dfl_kernels.cu after k_match.cuh). */
 #pragma once
 
-#ifndef RUN_SEGS
-#define RUN_SEGS 8 /* consecutive segments one CTA takes in a row (the first one sorts its window itself) */
-#endif
+#define RUN_SEGS_MAX 64 /* consecutive segments one CTA takes in a row at most (the first one sorts its window itself); the host picks the length */
 #define RUN_BLK 32768   /* block size = frame position of the segment */
 #define RUN_LOOKAHEAD 4 /* bytes past the segment staged with it: its last positions are hashed over their real 4 bytes */
 
