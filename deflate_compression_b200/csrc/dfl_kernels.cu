@@ -554,7 +554,7 @@ extern "C" int dfl_b200_deflate_finish(dfl_ctx *ctx, size_t *out_len, uint32_t *
             ctx->k_ms[ctx->ev_class[i]] += ms;
         }
     }
-    if (ctx->h_state->error) return DFL_E_SZ;
+    if (ctx->h_state->error) return ctx->h_state->error == 1 ? DFL_E_SZ : DFL_E_CUDA; /* 1: the output did not fit */
     if (out_len) *out_len = (size_t)ctx->h_state->total_out;
     if (adler) *adler = ctx->h_state->adler;
     return DFL_OK;
@@ -685,7 +685,7 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
         }
         CK(cudaStreamSynchronize(ctx->s_out));
         CK(cudaGetLastError());
-        if (ctx->h_state->error) return DFL_E_SZ;
+        if (ctx->h_state->error) return ctx->h_state->error == 1 ? DFL_E_SZ : DFL_E_CUDA;
         body = (size_t)ctx->h_state->total_out;
         adler = ctx->h_state->adler;
     }
@@ -760,7 +760,7 @@ extern "C" long dfl_b200_seg_index(dfl_ctx *ctx, uint64_t *offsets, long cap)
         if (cudaSetDevice(ctx->device) != cudaSuccess ||
             cudaMemcpy(offsets, ctx->seg_index, (size_t)cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess)
             return DFL_E_CUDA;
-        if (ctx->seg_index_n == 0) offsets[0] = 0;
+        if (ctx->seg_index_n == 0) offsets[0] = 5; /* empty input: the body is the lone empty stored block */
     }
     return cnt;
 }

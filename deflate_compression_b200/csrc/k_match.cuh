@@ -459,7 +459,8 @@ k_match(const uint8_t *__restrict__ d_in, long long n, long long avail_hist, lon
         if (!build_index<true>(S, soff, 0, 0, NI, gbuf, tid, lane, warp, state, sb)) {
             /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
             if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-            build_index<false>(S, soff, 0, 0, NI, gbuf, tid, lane, warp, state, sb);
+            if (!build_index<false>(S, soff, 0, 0, NI, gbuf, tid, lane, warp, state, sb) && tid == 0)
+                atomicExch(&state->error, 4u); /* the index is not in order either way (a scratch slot shared with another launch?): the call fails */
         }
     }
     const long long t2 = clock64();

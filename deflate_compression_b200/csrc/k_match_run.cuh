@@ -52,7 +52,8 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
         if (!build_index<true>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B)) {
             /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
             if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-            build_index<false>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B);
+            if (!build_index<false>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B) && tid == 0)
+                atomicExch(&state->error, 4u); /* not in order either way: the call fails rather than emit tokens from a wrong index */
         }
         for (int k8 = tid * 8; k8 < ni; k8 += MATCH_THREADS * 8)
             __stcg(reinterpret_cast<uint4 *>(saved[w] + k8), *reinterpret_cast<const uint4 *>(&S.list[k8]));

@@ -108,6 +108,9 @@ size_t dfl_b200_bound(const dfl_params *prm, size_t n);
  * Asynchronous on `stream` (a cudaStream_t, NULL = default) up to the final
  * size read-back; *out_len and *adler (Adler-32 of d_in[0,n) from start value
  * 1) are valid on return.
+ * Stored blocks are copied in aligned 4-byte words of d_in: up to 3 bytes before a segment's first byte and past
+ * d_in + n are read when they share an aligned word with the data -- never another word than the data's own, so
+ * any allocation that holds the data holds what is read (the match kernel stages exactly [d_in - hist_len, d_in + n)).
  */
 int dfl_b200_deflate_device(dfl_ctx *ctx, const uint8_t *d_in, size_t n, size_t hist_len,
                             int is_final, uint8_t *d_out, size_t out_cap, size_t *out_len,

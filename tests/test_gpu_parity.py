@@ -945,3 +945,13 @@ def test_split_through_the_reference_entry_point(D, O, tmp_path, monkeypatch):
     assert run(True) == z4
     monkeypatch.delenv("DFL_B200_SPLIT")
     assert run(False) == z0
+
+
+@pytest.mark.gpu
+def test_segment_index_of_an_empty_input(D, O):
+    """No segments: the index is its end entry alone, the length of the lone empty stored block."""
+    comp = D.Compressor()
+    z = comp.compress(np.zeros(0, dtype=np.uint8))
+    assert z == O.zlib_compress(np.zeros(0, dtype=np.uint8), O.params())
+    assert comp.seg_index().tolist() == [5]
+    comp.close()
