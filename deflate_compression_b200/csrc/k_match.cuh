@@ -92,10 +92,13 @@ __device__ __forceinline__ uint32_t cnt_shift(uint32_t d) { return (d & 1) * 16;
  *          group.  Stable by construction; several times slower (a vote costs ~3
  *          cycles of a unit shared by the whole SM).
  */
-template <int PASS, bool FAST>
+template <int PASS, bool FAST, bool BKC>
 __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int pos0, int lofs, int k_lo, int k_hi, int SS,
                                               const uint16_t *gbuf, int lane, int warp, int sb)
 {
+    /* BKC: the bucket of position pos0 + i is cached at S.list[DFL_MAX_SEG + i] (see build_index) */
+    uint32_t kbase = (uint32_t)__cvta_generic_to_shared(S.list) + 2 * DFL_MAX_SEG - 2 * (uint32_t)pos0;
+    asm volatile("" : "+r"(kbase));
     const uint32_t ss_inv = SS ? 0xFFFFFFFFu / (uint32_t)SS + 1u : 0u; /* x / SS == umulhi(x, ss_inv) for x * SS < 2^32 */
     const uint32_t ngrp = HASH_SIZE >> sb;
     /* pass-1 cursors at S.off[0..), pass-2 counters / cursors behind them */
@@ -120,7 +123,8 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int p
             const int k = k0 + j * 32 + lane;
             e[j] = PASS == 1 ? (uint32_t)(pos0 + k) : eq[j];
             if (PASS == 2 && k + 128 < k_hi) eq[j] = __ldcg(gbuf + k + 128);
-            const uint32_t b = hash4(ld4s(dbase + (k < k_hi ? e[j] : (uint32_t)pos0)), ngrp, sb);
+            const uint32_t b = BKC ? lds_u16(kbase + 2 * (k < k_hi ? e[j] : (uint32_t)pos0))
+                                   : hash4(ld4s(dbase + (k < k_hi ? e[j] : (uint32_t)pos0)), ngrp, sb);
             d[j] = PASS == 1 ? (b & (SORT_BINS - 1)) : (b / SORT_BINS);
             d2[j] = b / SORT_BINS;
         }
@@ -166,7 +170,7 @@ __device__ __forceinline__ void scatter_sweep(MatchSmem &S, uint32_t soff, int p
  * into one contiguous stripe per warp; counting is order free (shared memory
  * atomics), the scatter of a stripe is done in order by its warp.
  */
-template <int PASS, bool FAST>
+template <int PASS, bool FAST, bool BKC>
 __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int pos0, int lofs, int NI, const uint16_t *gbuf, int tid,
                                           int lane, int warp, DevState *state, int sb)
 {
@@ -189,14 +193,19 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int pos0,
         for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8) {
             const uint32_t w0 = ld4s(dbase + pos0 + k8), w1 = ld4s(dbase + pos0 + k8 + 4), w2 = ld4s(dbase + pos0 + k8 + 8);
             const uint32_t sw = __umulhi((uint32_t)k8, ss_inv); /* 8 | SS: the 8 positions share a stripe */
+            uint32_t bk[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
+                const uint32_t t = j < 4 ? __funnelshift_r(w0, w1, (j & 3) * 8) : __funnelshift_r(w1, w2, (j & 3) * 8);
+                bk[j] = hash4(t, ngrp, sb);
                 if (k8 + j < NI) {
-                    const uint32_t t = j < 4 ? __funnelshift_r(w0, w1, (j & 3) * 8) : __funnelshift_r(w1, w2, (j & 3) * 8);
-                    const uint32_t d = hash4(t, ngrp, sb) & (SORT_BINS - 1);
+                    const uint32_t d = bk[j] & (SORT_BINS - 1);
                     reds_add(cbase + 4 * cnt_word(sw, d), 1u << cnt_shift(d));
                 }
             }
+            if (BKC) /* the position's bucket is hashed once: both scatters and the offsets sweep read it back */
+                *reinterpret_cast<uint4 *>(&S.list[DFL_MAX_SEG + k8]) =
+                    make_uint4(bk[0] | (bk[1] << 16), bk[2] | (bk[3] << 16), bk[4] | (bk[5] << 16), bk[6] | (bk[7] << 16));
         }
         __syncthreads();
     }
@@ -216,7 +225,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int pos0,
     STAMP2(9);
     {
         const int k_lo = warp * SS, k_hi = (k_lo + SS < NI) ? k_lo + SS : NI;
-        scatter_sweep<PASS, FAST>(S, soff, pos0, lofs, k_lo, k_hi, SS, gbuf, lane, warp, sb);
+        scatter_sweep<PASS, FAST, BKC>(S, soff, pos0, lofs, k_lo, k_hi, SS, gbuf, lane, warp, sb);
     }
     __syncthreads();
     STAMP2(10);
@@ -226,7 +235,7 @@ __device__ __forceinline__ void sort_pass(MatchSmem &S, uint32_t soff, int pos0,
 /* Sort the NI positions [pos0, pos0 + NI) by (bucket, position) into S.list[lofs, lofs + NI) and fill the
  * bucket offsets (relative to lofs); bkt_out (global, optional) receives the bucket of every slot.  Returns (to
  * every thread) whether the order verified. */
-template <bool FAST>
+template <bool FAST, bool BKC = false>
 __device__ __noinline__ bool build_index(MatchSmem &S, uint32_t soff, int pos0, int lofs, int NI, uint16_t *gbuf, int tid, int lane,
                                             int warp, DevState *state, int sb, uint16_t *bkt_out = nullptr)
 {
@@ -234,16 +243,19 @@ __device__ __noinline__ bool build_index(MatchSmem &S, uint32_t soff, int pos0, 
     uint32_t dbase = (uint32_t)__cvta_generic_to_shared(S.data) + soff;
     uint32_t lbase = (uint32_t)__cvta_generic_to_shared(S.list) + 2 * lofs;
     uint32_t obase = (uint32_t)__cvta_generic_to_shared(S.off);
-    asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase));
+    /* BKC (k_match_run: lofs == 0 and NI <= DFL_MAX_SEG, the upper half of the list is free while a block is sorted):
+     * bucket of position pos0 + i cached at S.list[DFL_MAX_SEG + i] by pass 1's counting sweep */
+    uint32_t kbase = (uint32_t)__cvta_generic_to_shared(S.list) + 2 * DFL_MAX_SEG - 2 * (uint32_t)pos0;
+    asm volatile("" : "+r"(dbase), "+r"(lbase), "+r"(obase), "+r"(kbase));
     long long c0 = clock64(), c1;
 #define STAMP(slot) do { c1 = clock64(); if (tid == 0) atomicAdd(&state->t_phase[slot], (unsigned long long)(c1 - c0)); c0 = c1; } while (0)
-    sort_pass<1, FAST>(S, soff, pos0, lofs, NI, gbuf, tid, lane, warp, state, sb);
+    sort_pass<1, FAST, BKC>(S, soff, pos0, lofs, NI, gbuf, tid, lane, warp, state, sb);
     STAMP(4);
     /* park the pass-1 order in global scratch: linear, 16 B per thread */
     for (int k8 = tid * 8; k8 < NI; k8 += MATCH_THREADS * 8)
         __stcg(reinterpret_cast<uint4 *>(gbuf + k8), *reinterpret_cast<const uint4 *>(&S.list[lofs + k8]));
     STAMP(5);
-    sort_pass<2, FAST>(S, soff, pos0, lofs, NI, gbuf, tid, lane, warp, state, sb);
+    sort_pass<2, FAST, BKC>(S, soff, pos0, lofs, NI, gbuf, tid, lane, warp, state, sb);
     STAMP(6);
     /* bucket offsets from the sorted order (off[b] = first slot whose bucket is >= b), and
      * the check that every bucket is in ascending position order.  Slot kk is compared with
@@ -268,13 +280,14 @@ __device__ __noinline__ bool build_index(MatchSmem &S, uint32_t soff, int pos0, 
             q[0] = lo & 0xFFFF; q[1] = lo >> 16; q[2] = hi & 0xFFFF; q[3] = hi >> 16;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = kk0 + j < NI ? (int)hash4(ld4s(dbase + q[j]), ngrp, sb) : HASH_SIZE;
+        for (int j = 0; j < 4; j++)
+            b[j] = kk0 + j < NI ? (int)(BKC ? lds_u16(kbase + 2 * q[j]) : hash4(ld4s(dbase + q[j]), ngrp, sb)) : HASH_SIZE;
         /* k_match_run keeps every slot's bucket beside the list it saves for the next segment's merge */
         if (bkt_out && kk0 < NI) __stcg(reinterpret_cast<uint2 *>(bkt_out + kk0), make_uint2((uint32_t)b[0] | ((uint32_t)b[1] << 16), (uint32_t)b[2] | ((uint32_t)b[3] << 16)));
         int pq = __shfl_up_sync(FULL, q[3], 1), pb_ = __shfl_up_sync(FULL, b[3], 1);
         if (lane == 0) {
             pq = kk0 > 0 && kk0 <= NI ? (int)lds_u16(lbase + 2 * (kk0 - 1)) : -1;
-            pb_ = kk0 > 0 && kk0 <= NI ? (int)hash4(ld4s(dbase + pq), ngrp, sb) : -1;
+            pb_ = kk0 > 0 && kk0 <= NI ? (int)(BKC ? lds_u16(kbase + 2 * pq) : hash4(ld4s(dbase + pq), ngrp, sb)) : -1;
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {

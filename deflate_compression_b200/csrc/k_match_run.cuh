@@ -49,10 +49,10 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
 
     /* sort the ni positions from pos0 on, save the block (sorted positions, buckets, offsets) to slot w */
     auto sort_and_save = [&](int pos0, int ni, int sb, int w) {
-        if (!build_index<true>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B)) {
+        if (!build_index<true, true>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B)) {
             /* the atomics did not hand out slots in lane order: redo with the ballot-ranked scatter */
             if (tid == 0) atomicAdd(&state->sort_fallbacks, 1u);
-            if (!build_index<false>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B) && tid == 0)
+            if (!build_index<false, true>(S, soff, pos0, 0, ni, gbuf, tid, lane, warp, state, sb, saved[w] + B) && tid == 0)
                 atomicExch(&state->error, 4u); /* not in order either way: the call fails rather than emit tokens from a wrong index */
         }
         for (int k8 = tid * 8; k8 < ni; k8 += MATCH_THREADS * 8)
