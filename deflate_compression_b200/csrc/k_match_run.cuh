@@ -180,28 +180,46 @@ k_match_run(const uint8_t *__restrict__ d_in, long long n, long long avail_hist,
                 const uint16_t *wp = saved[w_win], *wb = wp + B, *sp = saved[w_seg], *sbk = sp + B;
                 /* a window entry at slot k of its list, bucket b, lands at k + (segment block's offset of b), less the
                  * position left out if that one's bucket comes before b */
-                for (int k4 = tid * 4; k4 < ni_win; k4 += MATCH_THREADS * 4) {
-                    const uint2 pp = __ldcg(reinterpret_cast<const uint2 *>(wp + k4)), bb = __ldcg(reinterpret_cast<const uint2 *>(wb + k4));
-                    const uint32_t pos[4] = {pp.x & 0xFFFF, pp.x >> 16, pp.y & 0xFFFF, pp.y >> 16};
-                    const uint32_t bk[4] = {bb.x & 0xFFFF, bb.x >> 16, bb.y & 0xFFFF, bb.y >> 16};
+                /* eight entries per thread and step (two 16-byte loads), the next step's loads issued before this step's stores */
+                {
+                    int k8 = tid * 8;
+                    uint4 pp = make_uint4(0, 0, 0, 0), bb = pp;
+                    if (k8 < ni_win) { pp = __ldcg(reinterpret_cast<const uint4 *>(wp + k8)); bb = __ldcg(reinterpret_cast<const uint4 *>(wb + k8)); }
+                    while (k8 < ni_win) {
+                        const int kn = k8 + MATCH_THREADS * 8;
+                        uint4 pn = make_uint4(0, 0, 0, 0), bn = pn;
+                        if (kn < ni_win) { pn = __ldcg(reinterpret_cast<const uint4 *>(wp + kn)); bn = __ldcg(reinterpret_cast<const uint4 *>(wb + kn)); }
+                        const uint32_t pw_[4] = {pp.x, pp.y, pp.z, pp.w}, bw_[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (k4 + j < ni_win) /* (a block saved as the segment's holds 32768 + position) */
-                            sts_u16(lbase + 2 * (k4 + j + lds_u16(obase + 2 * bk[j]) - ((int)bk[j] > b_drop ? 1 : 0)), pos[j] & (B - 1));
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t pos = (pw_[j >> 1] >> ((j & 1) * 16)) & 0xFFFF, bk = (bw_[j >> 1] >> ((j & 1) * 16)) & 0xFFFF;
+                            if (k8 + j < ni_win) /* (a block saved as the segment's holds 32768 + position) */
+                                sts_u16(lbase + 2 * (k8 + j + lds_u16(obase + 2 * bk) - ((int)bk > b_drop ? 1 : 0)), pos & (B - 1));
+                        }
+                        pp = pn; bb = bn; k8 = kn;
+                    }
                 }
                 __syncthreads();
                 /* S.off <- the window block's offsets; a segment entry at slot k, bucket b, lands at k + (window block's offset of b + 1) */
                 for (int b2 = tid; b2 < (HASH_SIZE + 2) / 2; b2 += MATCH_THREADS)
                     reinterpret_cast<uint32_t *>(S.off)[b2] = __ldcg(reinterpret_cast<const uint32_t *>(wp + 2 * B) + b2);
                 __syncthreads();
-                for (int k4 = tid * 4; k4 < ni_seg; k4 += MATCH_THREADS * 4) {
-                    const uint2 pp = __ldcg(reinterpret_cast<const uint2 *>(sp + k4)), bb = __ldcg(reinterpret_cast<const uint2 *>(sbk + k4));
-                    const uint32_t pos[4] = {pp.x & 0xFFFF, pp.x >> 16, pp.y & 0xFFFF, pp.y >> 16};
-                    const uint32_t bk[4] = {bb.x & 0xFFFF, bb.x >> 16, bb.y & 0xFFFF, bb.y >> 16};
+                {
+                    int k8 = tid * 8;
+                    uint4 pp = make_uint4(0, 0, 0, 0), bb = pp;
+                    if (k8 < ni_seg) { pp = __ldcg(reinterpret_cast<const uint4 *>(sp + k8)); bb = __ldcg(reinterpret_cast<const uint4 *>(sbk + k8)); }
+                    while (k8 < ni_seg) {
+                        const int kn = k8 + MATCH_THREADS * 8;
+                        uint4 pn = make_uint4(0, 0, 0, 0), bn = pn;
+                        if (kn < ni_seg) { pn = __ldcg(reinterpret_cast<const uint4 *>(sp + kn)); bn = __ldcg(reinterpret_cast<const uint4 *>(sbk + kn)); }
+                        const uint32_t pw_[4] = {pp.x, pp.y, pp.z, pp.w}, bw_[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int kk = k4 + j;
-                        if (kk < ni_seg && kk != k_drop) sts_u16(lbase + 2 * (kk - (kk > k_drop ? 1 : 0) + lds_u16(obase + 2 * bk[j] + 2)), pos[j]);
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t pos = (pw_[j >> 1] >> ((j & 1) * 16)) & 0xFFFF, bk = (bw_[j >> 1] >> ((j & 1) * 16)) & 0xFFFF;
+                            const int kk = k8 + j;
+                            if (kk < ni_seg && kk != k_drop) sts_u16(lbase + 2 * (kk - (kk > k_drop ? 1 : 0) + lds_u16(obase + 2 * bk + 2)), pos);
+                        }
+                        pp = pn; bb = bn; k8 = kn;
                     }
                 }
                 __syncthreads();
