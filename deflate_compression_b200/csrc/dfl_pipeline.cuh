@@ -11,6 +11,8 @@
 #include <thread>
 
 #include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -123,15 +125,39 @@ static size_t fd_piece_len(size_t piece, size_t seg, long i)
     return p < piece ? p : piece;
 }
 
-/* write(2) of one output piece; a regular file takes it from several threads with pwrite(2) */
+/* One output piece to fd_out.  A regular file that can be mapped (opened read-write: a memfd, a file opened O_RDWR) is
+ * grown with fallocate(2) and filled through a shared mapping by several threads -- plain copies at memory speed;
+ * write(2) / pwrite(2) into the page cache take a lock per page and stop at ~5 GB/s however many threads call them
+ * (measured: the writer was what bounded the fd -> fd call).  Anything else: pwrite(2) from several threads, or write(2). */
 static int fd_write_piece(int fd, bool regular, unsigned long long file_off, const uint8_t *p, size_t n)
 {
-    if (!regular || n < (8u << 20)) {
+    if (!regular || n < (1u << 20)) {
         if (regular && lseek(fd, (off_t)file_off, SEEK_SET) < 0) return -1;
         return fd_write_all(fd, p, n);
     }
     const int nt = FD_IO_THREADS;
     const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+    {
+        struct stat st;
+        const unsigned long long end = file_off + n, map_lo = file_off & ~4095ull;
+        /* fallocate(2) grows the file AND reserves its pages: a store through the mapping can then not run out of
+         * space (which would be a SIGBUS, not an error return) */
+        if (fstat(fd, &st) == 0 && fallocate(fd, 0, (off_t)file_off, (off_t)n) == 0) {
+            void *m = mmap(NULL, (size_t)(end - map_lo), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_lo);
+            if (m != MAP_FAILED) {
+                uint8_t *dst = (uint8_t *)m + (file_off - map_lo);
+                std::vector<std::thread> th;
+                for (int t = 0; t < nt; t++) {
+                    const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+                    if (lo >= hi) break;
+                    th.emplace_back([=] { memcpy(dst + lo, p + lo, hi - lo); });
+                }
+                for (auto &t : th) t.join();
+                munmap(m, (size_t)(end - map_lo));
+                return lseek(fd, (off_t)end, SEEK_SET) < 0 ? -1 : 0; /* as write(2) would have left it */
+            }
+        }
+    }
     bool bad = false;
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) {
@@ -153,6 +179,20 @@ static int fd_write_piece(int fd, bool regular, unsigned long long file_off, con
 }
 
 namespace {
+/* DFL_B200_FD_TRACE=1: a line per pipeline event on stderr (ms since the call began) -- where an fd -> fd call spends its time */
+struct FdTrace {
+    bool on;
+    double t0;
+    std::mutex mu;
+    static double now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    FdTrace() : on(getenv("DFL_B200_FD_TRACE") && atoi(getenv("DFL_B200_FD_TRACE"))), t0(now()) {}
+    void ev(const char *what, long i, size_t n = 0)
+    {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(mu);
+        fprintf(stderr, "[fd %8.3f ms] %-14s piece %ld (%zu B)\n", now() - t0, what, i, n);
+    }
+};
 struct FdPipe {
     std::mutex mu;
     std::condition_variable cv;
@@ -203,6 +243,7 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
     }
 
     FdPipe P;
+    FdTrace T;
     std::thread reader([&] {
         unsigned long long off = start_off;
         for (long i = 0;; i++) {
@@ -213,7 +254,9 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
             }
             const int s = (int)(i % FD_IN_SLOTS);
             const size_t want = fd_piece_len(piece, (size_t)prm.seg_bytes, i);
+            T.ev("read begin", i, want);
             const long long got = fd_read_piece(fd_in, regular, off, ctx->fd_h_in[s], want);
+            T.ev("read end", i, got > 0 ? (size_t)got : 0);
             std::lock_guard<std::mutex> lk(P.mu);
             if (got < 0) { P.in_err = true; P.in_eof = true; P.cv.notify_all(); return; }
             off += (unsigned long long)got;
@@ -244,7 +287,9 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
                 if (P.out_ready <= j) return;
                 len = P.out_len[j % FD_OUT_SLOTS];
             }
+            T.ev("write begin", j, len);
             if (!bad && fd_out >= 0 && fd_write_piece(fd_out, regular_out, woff, ctx->fd_h_out[j % FD_OUT_SLOTS], len) != 0) bad = true;
+            T.ev("write end", j, len);
             woff += len;
             std::lock_guard<std::mutex> lk(P.mu);
             P.out_done = j + 1;
@@ -291,18 +336,22 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
             last = len_next == 0;
         }
         if (cudaStreamWaitEvent(ctx->s_run, ctx->fd_e_in[ds], 0) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+        T.ev("enqueue", i, len);
         rc = dfl_b200_deflate_enqueue(ctx, ctx->fd_d_in[ds] + W, len, hist, last ? 1 : 0, ctx->fd_d_out[ds], bound, ctx->s_run);
         if (rc) break;
+        T.ev("enqueued", i, len);
         /* while piece i is compressed: piece i + 1 goes to the device, piece i - 1 goes to the writer */
         if (!last && !copy_in(i + 1, len_next, len)) { rc = DFL_E_CUDA; break; }
         if (i > 0) {
             if (cudaEventSynchronize(ctx->fd_e_out[ds ^ 1]) != cudaSuccess) { rc = DFL_E_CUDA; break; }
+            T.ev("d2h done", i - 1, body_prev);
             publish(i - 1, body_prev);
         }
         size_t body = 0;
         uint32_t a = 1;
         rc = dfl_b200_deflate_finish(ctx, &body, &a, ctx->s_run);
         if (rc) break;
+        T.ev("kernels done", i, body);
         adler = dfl_b200_adler32_combine(adler, a, len);
         total_in += len;
         {
@@ -338,6 +387,7 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
     }
     reader.join();
     writer.join();
+    T.ev("joined", -1);
     if (regular) lseek(fd_in, (off_t)(start_off + total_in), SEEK_SET); /* as read(2) would have left it */
     cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->s_run);

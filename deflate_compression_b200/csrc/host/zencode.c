@@ -58,7 +58,8 @@ int main(int argc, char *argv[])
         fprintf(stderr, "%s: no such file\n", files[0]);
         return 1;
     }
-    if (files[1] && (fd_out = open(files[1], O_WRONLY | O_CREAT | O_TRUNC, 0644)) < 0) {
+    /* (read-write: the compressor fills a mappable output file through a shared mapping) */
+    if (files[1] && (fd_out = open(files[1], O_RDWR | O_CREAT | O_TRUNC, 0644)) < 0) {
         fprintf(stderr, "%s: cannot create\n", files[1]);
         return 1;
     }

@@ -955,3 +955,43 @@ def test_segment_index_of_an_empty_input(D, O):
     assert z == O.zlib_compress(np.zeros(0, dtype=np.uint8), O.params())
     assert comp.seg_index().tolist() == [5]
     comp.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,piece", [(5 << 20, 1 << 20), (40 << 20, 8 << 20), (3 * 65536 + 1, 65536)])
+def test_fd_pipeline_mapped_output(D, O, tmp_path, n, piece):
+    """An output fd that can be mapped (opened read-write: a regular file, a memfd) is filled through a shared mapping
+    instead of pwrite(2): same bytes, the file offset left where write(2) would have left it, also when the output does
+    not start at offset 0 and when the file already holds more bytes than the stream (nothing is truncated)."""
+    data = make_input("markov", 92, 0, n)
+    comp = D.Compressor()
+    want = comp.compress(data)
+    src = tmp_path / "in"
+    src.write_bytes(data.tobytes())
+    # regular file, read-write, output appended after 4099 bytes that are already there
+    dst = tmp_path / "out.z"
+    dst.write_bytes(b"x" * 4099)
+    fi, fo = os.open(src, os.O_RDONLY), os.open(dst, os.O_RDWR)
+    try:
+        os.lseek(fo, 4099, os.SEEK_SET)
+        nin, nout = comp.compress_fd(fi, fo, piece)
+        assert (nin, nout) == (n, len(want))
+        assert os.lseek(fo, 0, os.SEEK_CUR) == 4099 + len(want)
+    finally:
+        os.close(fi), os.close(fo)
+    got = dst.read_bytes()
+    assert got[:4099] == b"x" * 4099 and got[4099:] == want
+    # memfd, written twice: the second stream is shorter than what the file holds
+    mi, mo = os.memfd_create("in"), os.memfd_create("out")
+    try:
+        os.write(mi, data.tobytes())
+        for m in (n, n // 2):
+            os.ftruncate(mi, m)
+            os.lseek(mi, 0, os.SEEK_SET), os.lseek(mo, 0, os.SEEK_SET)
+            nin, nout = comp.compress_fd(mi, mo, piece)
+            z = os.pread(mo, nout, 0)
+            assert nin == m and zlib.decompress(z) == data[:m].tobytes()
+            assert os.lseek(mo, 0, os.SEEK_CUR) == nout
+    finally:
+        os.close(mi), os.close(mo)
+    comp.close()
