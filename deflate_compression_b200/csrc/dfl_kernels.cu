@@ -636,6 +636,9 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
         CK(cudaMemcpyAsync(out + 2, d_body, body, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     } else {
+        /* (every error exit drains the three streams before it returns: copies from `in` and into `out` may be in
+         * flight, and the caller is free to release its buffers once the call has failed) */
+        const int prc = [&]() -> int {
         /* pipeline over pieces: copy-in of piece i+1, kernels of piece i and copy-out of piece i-1 overlap
          * on three streams; output offsets stay on the device, each piece's end offset comes back with it */
         int rc = ensure_ws(ctx, piece_segs);
@@ -688,6 +691,15 @@ extern "C" int dfl_b200_compress_host(dfl_ctx *ctx, const uint8_t *in, size_t n,
         if (ctx->h_state->error) return ctx->h_state->error == 1 ? DFL_E_SZ : DFL_E_CUDA;
         body = (size_t)ctx->h_state->total_out;
         adler = ctx->h_state->adler;
+            return DFL_OK;
+        }();
+        if (prc) {
+            cudaStreamSynchronize(ctx->s_in);
+            cudaStreamSynchronize(ctx->s_run);
+            cudaStreamSynchronize(ctx->s_out);
+            cudaGetLastError();
+            return prc;
+        }
     }
 #undef PIECE_S0
 #undef PIECE_S1
