@@ -68,6 +68,8 @@ struct dfl_ctx {
     uint8_t *fd_h_in[3], *fd_h_out[2], *fd_d_in[2], *fd_d_out[2];
     cudaEvent_t fd_e_in[2], fd_e_out[2];
     size_t fd_piece, fd_piece_req;
+    uint8_t *mh_in, *mh_out; /* dfl_b200_compress_fd_multi (kept by the first context): pinned whole-input / whole-output buffers */
+    size_t mh_in_cap, mh_out_cap;
     int parse_mode; /* 0 = by segment count, 1 = k_parse_warp, 2 = k_parse */
     int match_mode; /* 0 = k_match_run where the geometry allows, 1 = always k_match */
     int num_sms;
@@ -309,6 +311,8 @@ extern "C" void dfl_b200_destroy(dfl_ctx *ctx)
     if (ctx->inf_w) cudaFree(ctx->inf_w);
     if (ctx->d_png) cudaFree(ctx->d_png);
     fd_free(ctx);
+    if (ctx->mh_in) cudaFreeHost(ctx->mh_in);
+    if (ctx->mh_out) cudaFreeHost(ctx->mh_out);
     for (int i = 0; i < ctx->pipe_cap; i++) { cudaEventDestroy(ctx->e_in[i]); cudaEventDestroy(ctx->e_done[i]); }
     free(ctx->e_in); free(ctx->e_done);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);

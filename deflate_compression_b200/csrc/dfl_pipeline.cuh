@@ -109,6 +109,27 @@ static void fd_free(dfl_ctx *ctx)
     }
 }
 
+/* pinned host pieces and device slots of the fd pipelines live with the context */
+static int fd_slots_init(dfl_ctx *ctx, size_t piece, size_t bound)
+{
+    const size_t W = DFL_MAX_WINDOW;
+    if (ctx->fd_h_in[0] && ctx->fd_piece != piece) fd_free(ctx); /* (piece or segment size changed between calls) */
+    if (!ctx->fd_h_in[0]) {
+        for (int s = 0; s < FD_IN_SLOTS; s++) CK(cudaMallocHost(&ctx->fd_h_in[s], piece));
+        for (int s = 0; s < FD_OUT_SLOTS; s++) CK(cudaMallocHost(&ctx->fd_h_out[s], bound + 16));
+        for (int s = 0; s < 2; s++) {
+            CK(cudaMalloc(&ctx->fd_d_in[s], W + piece + 32));
+            CK(cudaMalloc(&ctx->fd_d_out[s], bound));
+        }
+        for (int s = 0; s < 2; s++) {
+            CK(cudaEventCreateWithFlags(&ctx->fd_e_in[s], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->fd_e_out[s], cudaEventDisableTiming));
+        }
+        ctx->fd_piece = piece;
+    }
+    return DFL_OK;
+}
+
 extern "C" int dfl_b200_set_fd_piece(dfl_ctx *ctx, size_t bytes)
 {
     if (!ctx) return DFL_E_INVAL;
@@ -143,7 +164,7 @@ static int fd_write_piece(int fd, bool regular, unsigned long long file_off, con
         /* fallocate(2) grows the file AND reserves its pages: a store through the mapping can then not run out of
          * space (which would be a SIGBUS, not an error return) */
         if (fstat(fd, &st) == 0 && fallocate(fd, 0, (off_t)file_off, (off_t)n) == 0) {
-            void *m = mmap(NULL, (size_t)(end - map_lo), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_lo);
+            void *m = mmap(NULL, (size_t)(end - map_lo), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, (off_t)map_lo); /* (populated in one go: a fault per page from the copying threads costs more) */
             if (m != MAP_FAILED) {
                 uint8_t *dst = (uint8_t *)m + (file_off - map_lo);
                 std::vector<std::thread> th;
@@ -219,21 +240,8 @@ extern "C" int dfl_b200_compress_fd(dfl_ctx *ctx, int fd_in, int fd_out, unsigne
     const size_t W = DFL_MAX_WINDOW, bound = dfl_b200_bound(&prm, piece) + 16;
     int rc = host_pipe_init(ctx, 1); /* the three streams */
     if (rc) return rc;
-    /* pinned host pieces and device slots live with the context */
-    if (ctx->fd_h_in[0] && ctx->fd_piece != piece) fd_free(ctx); /* (piece or segment size changed between calls) */
-    if (!ctx->fd_h_in[0]) {
-        for (int s = 0; s < FD_IN_SLOTS; s++) CK(cudaMallocHost(&ctx->fd_h_in[s], piece));
-        for (int s = 0; s < FD_OUT_SLOTS; s++) CK(cudaMallocHost(&ctx->fd_h_out[s], bound + 16));
-        for (int s = 0; s < 2; s++) {
-            CK(cudaMalloc(&ctx->fd_d_in[s], W + piece + 32));
-            CK(cudaMalloc(&ctx->fd_d_out[s], bound));
-        }
-        for (int s = 0; s < 2; s++) {
-            CK(cudaEventCreateWithFlags(&ctx->fd_e_in[s], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ctx->fd_e_out[s], cudaEventDisableTiming));
-        }
-        ctx->fd_piece = piece;
-    }
+    rc = fd_slots_init(ctx, piece, bound);
+    if (rc) return rc;
     struct stat st_in;
     const bool regular = fstat(fd_in, &st_in) == 0 && S_ISREG(st_in.st_mode);
     unsigned long long start_off = 0;
@@ -475,5 +483,238 @@ extern "C" int dfl_b200_compress_host_multi(dfl_ctx **ctxs, int ndev, const uint
     out[pos + 2] = (uint8_t)(adler >> 8);
     out[pos + 3] = (uint8_t)adler;
     *out_len = pos + 4;
+    return DFL_OK;
+}
+
+/*
+ * fd -> fd on N GPUs: what deflate_compress() runs when DFL_B200_DEVICES names more than one device.  The pipeline of
+ * dfl_b200_compress_fd with the pieces dealt round the contexts: piece i goes to context i mod N, primed with the 32 KiB
+ * before it from the pinned slot piece i - 1 was read into (no device-to-device copy); N pieces are in flight, one per
+ * context; they are retired in order (size and Adler-32 read back, body copied out, handed to the writer thread).  The
+ * reader thread, the writer thread and the pinned slots are the single-device call's (3 input and 2 output slots per
+ * context, all used as one ring).  Byte-identical to the one-GPU calls.
+ */
+extern "C" int dfl_b200_compress_fd_multi(dfl_ctx **ctxs, int ndev, int fd_in, int fd_out, unsigned long long *in_bytes,
+                                          unsigned long long *out_bytes)
+{
+    if (!ctxs || ndev < 1 || !ctxs[0]) return DFL_E_INVAL;
+    if (ndev == 1) return dfl_b200_compress_fd(ctxs[0], fd_in, fd_out, in_bytes, out_bytes);
+    for (int r = 0; r < ndev; r++)
+        if (!ctxs[r] || memcmp(&ctxs[r]->prm, &ctxs[0]->prm, sizeof(dfl_params)) != 0) return DFL_E_INVAL;
+    dfl_ctx *ctx = ctxs[0];
+    const dfl_params prm = ctx->prm;
+    size_t piece = (ctx->fd_piece_req ? ctx->fd_piece_req : (size_t)FD_PIECE_BYTES) / (size_t)prm.seg_bytes * (size_t)prm.seg_bytes;
+    if (piece < (size_t)prm.seg_bytes) piece = (size_t)prm.seg_bytes;
+    if (piece < DFL_MAX_WINDOW) piece = (DFL_MAX_WINDOW + (size_t)prm.seg_bytes - 1) / (size_t)prm.seg_bytes * (size_t)prm.seg_bytes;
+    const size_t W = DFL_MAX_WINDOW, bound = dfl_b200_bound(&prm, piece) + 16;
+    const int NIN = FD_IN_SLOTS * ndev, NOUT = FD_OUT_SLOTS * ndev;
+    std::vector<uint8_t *> h_in(NIN), h_out(NOUT);
+    for (int r = 0; r < ndev; r++) {
+        ctx = ctxs[r];
+        CK(cudaSetDevice(ctx->device));
+        int rc = host_pipe_init(ctx, 1);
+        if (rc) return rc;
+        rc = fd_slots_init(ctx, piece, bound);
+        if (rc) return rc;
+        for (int s = 0; s < FD_IN_SLOTS; s++) h_in[r * FD_IN_SLOTS + s] = ctx->fd_h_in[s];
+        for (int s = 0; s < FD_OUT_SLOTS; s++) h_out[r * FD_OUT_SLOTS + s] = ctx->fd_h_out[s];
+    }
+    ctx = ctxs[0];
+    struct stat st_in;
+    const bool regular = fstat(fd_in, &st_in) == 0 && S_ISREG(st_in.st_mode);
+    unsigned long long start_off = 0;
+    if (regular) {
+        const off_t cur = lseek(fd_in, 0, SEEK_CUR);
+        start_off = cur > 0 ? (unsigned long long)cur : 0;
+    }
+    /* shared with the two threads (the ring sizes differ from FdPipe's) */
+    std::mutex mu;
+    std::condition_variable cv;
+    long in_ready = 0, in_free = 0, out_ready = 0, out_done = 0;
+    std::vector<size_t> in_len(NIN, 0), out_len(NOUT, 0);
+    bool in_eof = false, in_err = false, out_err = false, out_close = false;
+    FdTrace T;
+    std::thread reader([&] {
+        unsigned long long off = start_off;
+        for (long i = 0;; i++) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return i - in_free < NIN || out_err; });
+                if (out_err) return;
+            }
+            const int s = (int)(i % NIN);
+            const size_t want = fd_piece_len(piece, (size_t)prm.seg_bytes, i);
+            T.ev("read begin", i, want);
+            const long long got = fd_read_piece(fd_in, regular, off, h_in[s], want);
+            T.ev("read end", i, got > 0 ? (size_t)got : 0);
+            std::lock_guard<std::mutex> lk(mu);
+            if (got < 0) { in_err = true; in_eof = true; cv.notify_all(); return; }
+            off += (unsigned long long)got;
+            in_len[s] = (size_t)got;
+            in_ready = i + 1;
+            if ((size_t)got < want) in_eof = true;
+            cv.notify_all();
+            if ((size_t)got < want) return;
+        }
+    });
+    struct stat st_out;
+    const bool regular_out = fd_out >= 0 && fstat(fd_out, &st_out) == 0 && S_ISREG(st_out.st_mode);
+    unsigned long long out_off = 0;
+    if (regular_out) {
+        const off_t cur = lseek(fd_out, 0, SEEK_CUR);
+        out_off = cur > 0 ? (unsigned long long)cur : 0;
+    }
+    std::thread writer([&] {
+        static const uint8_t hdr[2] = {0x78, 0x9C};
+        bool bad = fd_out >= 0 && fd_write_all(fd_out, hdr, 2) != 0;
+        unsigned long long woff = out_off + 2;
+        for (long j = 0;; j++) {
+            size_t len;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (bad) { out_err = true; cv.notify_all(); }
+                cv.wait(lk, [&] { return out_ready > j || out_close; });
+                if (out_ready <= j) return;
+                len = out_len[j % NOUT];
+            }
+            T.ev("write begin", j, len);
+            if (!bad && fd_out >= 0 && fd_write_piece(fd_out, regular_out, woff, h_out[j % NOUT], len) != 0) bad = true;
+            T.ev("write end", j, len);
+            woff += len;
+            std::lock_guard<std::mutex> lk(mu);
+            out_done = j + 1;
+            if (bad) out_err = true;
+            cv.notify_all();
+        }
+    });
+
+    unsigned long long total_in = 0, total_out = 2;
+    uint32_t adler = 1;
+    int rc = DFL_OK;
+    std::vector<size_t> plen; /* length of every piece seen so far */
+    long n_pieces = -1;       /* known once the last piece has been seen */
+    auto wait_piece = [&](long i, size_t *len) -> bool { /* the reader has delivered piece i (or reached the end before it) */
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return in_ready > i || in_err || in_eof; });
+        if (in_err) return false;
+        *len = in_ready > i ? in_len[i % NIN] : 0;
+        return true;
+    };
+    auto publish = [&](long j, size_t olen) {
+        std::lock_guard<std::mutex> lk(mu);
+        out_len[j % NOUT] = olen;
+        out_ready = j + 1;
+        cv.notify_all();
+    };
+    /* piece i to its context: the window from the slot of piece i - 1, the piece itself, then the kernels */
+    auto stage = [&](long i) -> int {
+        dfl_ctx *c = ctxs[i % ndev];
+        const int ds = (int)((i / ndev) & 1);
+        if (cudaSetDevice(c->device) != cudaSuccess) return DFL_E_CUDA;
+        uint8_t *d_piece = c->fd_d_in[ds] + W;
+        const size_t len = plen[i], before = i ? plen[i - 1] : 0, hist = before < W ? before : W;
+        if (hist && cudaMemcpyAsync(d_piece - hist, h_in[(i - 1) % NIN] + before - hist, hist, cudaMemcpyHostToDevice, c->s_in) != cudaSuccess) return DFL_E_CUDA;
+        if (len && cudaMemcpyAsync(d_piece, h_in[i % NIN], len, cudaMemcpyHostToDevice, c->s_in) != cudaSuccess) return DFL_E_CUDA;
+        return cudaEventRecord(c->fd_e_in[ds], c->s_in) == cudaSuccess ? DFL_OK : DFL_E_CUDA;
+    };
+    auto enqueue = [&](long i) -> int {
+        dfl_ctx *c = ctxs[i % ndev];
+        const int ds = (int)((i / ndev) & 1);
+        if (cudaSetDevice(c->device) != cudaSuccess) return DFL_E_CUDA;
+        const size_t before = i ? plen[i - 1] : 0, hist = before < W ? before : W;
+        if (cudaStreamWaitEvent(c->s_run, c->fd_e_in[ds], 0) != cudaSuccess) return DFL_E_CUDA;
+        T.ev("enqueue", i, plen[i]);
+        return dfl_b200_deflate_enqueue(c, c->fd_d_in[ds] + W, plen[i], hist, i == n_pieces - 1 ? 1 : 0, c->fd_d_out[ds], bound, c->s_run);
+    };
+    long pending_pub = -1; /* piece whose body is on its way to its pinned slot */
+    size_t pending_len = 0;
+    auto flush_pub = [&]() -> int {
+        if (pending_pub < 0) return DFL_OK;
+        dfl_ctx *c = ctxs[pending_pub % ndev];
+        if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->fd_e_out[(pending_pub / ndev) & 1]) != cudaSuccess) return DFL_E_CUDA;
+        T.ev("d2h done", pending_pub, pending_len);
+        if (pending_pub == n_pieces - 1) { /* RFC 1950: Adler-32 of the uncompressed data, MSB first */
+            uint8_t *ho = h_out[pending_pub % NOUT] + pending_len;
+            ho[0] = (uint8_t)(adler >> 24); ho[1] = (uint8_t)(adler >> 16); ho[2] = (uint8_t)(adler >> 8); ho[3] = (uint8_t)adler;
+            pending_len += 4;
+            total_out += 4;
+        }
+        publish(pending_pub, pending_len);
+        pending_pub = -1;
+        return DFL_OK;
+    };
+    auto retire = [&](long j) -> int {
+        dfl_ctx *c = ctxs[j % ndev];
+        const int ds = (int)((j / ndev) & 1);
+        if (cudaSetDevice(c->device) != cudaSuccess) return DFL_E_CUDA;
+        size_t body = 0;
+        uint32_t a = 1;
+        int r_ = dfl_b200_deflate_finish(c, &body, &a, c->s_run);
+        if (r_) return r_;
+        T.ev("kernels done", j, body);
+        adler = dfl_b200_adler32_combine(adler, a, plen[j]);
+        total_in += plen[j];
+        r_ = flush_pub(); /* (the piece before: its copy out had this piece's kernels to hide behind) */
+        if (r_) return r_;
+        {
+            /* the slot of piece j - 1 can be read into again (piece j's copy in, which read its tail, is done); piece
+             * j's output slot must have been written out */
+            std::unique_lock<std::mutex> lk(mu);
+            in_free = j;
+            cv.notify_all();
+            cv.wait(lk, [&] { return out_done >= j - (NOUT - 1) || out_err; });
+            if (out_err) return DFL_E_INVAL;
+        }
+        if (body && cudaMemcpyAsync(h_out[j % NOUT], c->fd_d_out[ds], body, cudaMemcpyDeviceToHost, c->s_out) != cudaSuccess) return DFL_E_CUDA;
+        if (cudaEventRecord(c->fd_e_out[ds], c->s_out) != cudaSuccess) return DFL_E_CUDA;
+        total_out += body;
+        pending_pub = j;
+        pending_len = body;
+        return DFL_OK;
+    };
+    for (long i = 0; rc == DFL_OK; i++) {
+        if (n_pieces < 0) {
+            /* piece i, and whether it is the last one (a piece that fills its slot is followed by another read) */
+            size_t len = 0, nxt = 0;
+            if ((long)plen.size() <= i) {
+                if (!wait_piece(i, &len)) { rc = DFL_E_INVAL; break; }
+                plen.push_back(len);
+            }
+            bool last = plen[i] < fd_piece_len(piece, (size_t)prm.seg_bytes, i);
+            if (!last) {
+                if (!wait_piece(i + 1, &nxt)) { rc = DFL_E_INVAL; break; }
+                if (nxt == 0) last = true; else plen.push_back(nxt);
+            }
+            if (last) n_pieces = i + 1;
+            rc = stage(i);
+            if (rc) break;
+        } else if (i >= n_pieces + ndev) {
+            break;
+        }
+        if (i >= ndev && i - ndev < (n_pieces < 0 ? i : n_pieces)) { rc = retire(i - ndev); if (rc) break; }
+        if (n_pieces < 0 || i < n_pieces) { rc = enqueue(i); if (rc) break; }
+    }
+    if (rc == DFL_OK) rc = flush_pub();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        out_close = true;
+        if (rc) out_err = true; /* releases the reader */
+        in_free = 1L << 60;
+        cv.notify_all();
+    }
+    reader.join();
+    writer.join();
+    T.ev("joined", -1);
+    if (regular) lseek(fd_in, (off_t)(start_off + total_in), SEEK_SET); /* as read(2) would have left it */
+    for (int r = 0; r < ndev; r++) {
+        cudaSetDevice(ctxs[r]->device);
+        cudaStreamSynchronize(ctxs[r]->s_in);
+        cudaStreamSynchronize(ctxs[r]->s_run);
+        cudaStreamSynchronize(ctxs[r]->s_out);
+    }
+    if (rc) return rc;
+    if (out_err || in_err) return DFL_E_INVAL;
+    if (in_bytes) *in_bytes = total_in;
+    if (out_bytes) *out_bytes = total_out;
     return DFL_OK;
 }

@@ -47,7 +47,8 @@ static int parked_window, parked_device, parked_atexit;
 /* The reference's entry points have no device argument: DFL_B200_DEVICE (default 0) picks the GPU. */
 static int env_device(void)
 {
-    const char *e = getenv("DFL_B200_DEVICE");
+    const char *e = getenv("DFL_B200_DEVICE"), *m = getenv("DFL_B200_DEVICES");
+    if (m && *m) return atoi(m); /* a device list: its first entry */
     return e && *e ? atoi(e) : 0;
 }
 
@@ -59,11 +60,35 @@ static int env_block_mode(void)
     return e && *e && atoi(e) ? 4 : 0;
 }
 
+/* DFL_B200_DEVICES=0,1,2,...: more than one device puts every call without a record stream on all of them
+ * (contiguous shards, one zlib stream: dfl_b200_compress_fd_multi).  The extra contexts stay parked like the first. */
+#define MULTI_MAX 16
+static dfl_ctx *multi_ctx[MULTI_MAX]; /* contexts on devices 1.. of the list ([0] is the call's own) */
+static int multi_dev[MULTI_MAX], multi_n;
+
+static int env_devices(int *devs)
+{
+    const char *e = getenv("DFL_B200_DEVICES");
+    int k = 0;
+    while (e && *e && k < MULTI_MAX) {
+        char *end;
+        const long v = strtol(e, &end, 10);
+        if (end == e) break;
+        devs[k++] = (int)v;
+        e = *end == ',' ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    return k;
+}
+
 static void parked_release(void)
 {
+    int i;
     pthread_mutex_lock(&parked_mu);
     dfl_b200_destroy(parked_ctx);
     parked_ctx = NULL;
+    for (i = 0; i < MULTI_MAX; i++) { dfl_b200_destroy(multi_ctx[i]); multi_ctx[i] = NULL; }
+    multi_n = 0;
     pthread_mutex_unlock(&parked_mu);
 }
 
@@ -199,14 +224,41 @@ static int deflate_compr_run(deflate_compr_t *com)
     int rc;
     dfl_params prm;
     if (com->err) return com->err;
-    /* no record stream wanted: the pipelined fd -> fd path (reads, copies, kernels and writes overlap) */
-    if (com->fd_stats < 0) return map_err(dfl_b200_compress_fd(com->ctx, com->fd_in, com->fd_out, NULL, NULL));
+    if (com->fd_stats < 0) {
+        /* no record stream wanted.  Several devices named: the whole input, sharded over them */
+        int devs[MULTI_MAX];
+        const int nd = env_devices(devs);
+        if (nd > 1) {
+            dfl_ctx *ctxs[MULTI_MAX];
+            int i;
+            dfl_b200_default_params(&prm);
+            prm.window = com->sliding_window;
+            prm.block_mode = env_block_mode();
+            ctxs[0] = com->ctx; /* made on the first device of the list (env_device) */
+            rc = 0;
+            pthread_mutex_lock(&parked_mu);
+            for (i = 1; i < nd && !rc; i++) {
+                if (multi_ctx[i] && multi_dev[i] != devs[i]) { dfl_b200_destroy(multi_ctx[i]); multi_ctx[i] = NULL; }
+                if (!multi_ctx[i]) rc = map_err(dfl_b200_create(&multi_ctx[i], devs[i], &prm));
+                else rc = map_err(dfl_b200_set_params(multi_ctx[i], &prm));
+                multi_dev[i] = devs[i];
+                ctxs[i] = multi_ctx[i];
+            }
+            if (!parked_atexit) { parked_atexit = 1; atexit(parked_release); }
+            if (!rc) rc = map_err(dfl_b200_compress_fd_multi(ctxs, nd, com->fd_in, com->fd_out, NULL, NULL));
+            pthread_mutex_unlock(&parked_mu);
+            return rc;
+        }
+        /* one device: the pipelined fd -> fd path (reads, copies, kernels and writes overlap) */
+        return map_err(dfl_b200_compress_fd(com->ctx, com->fd_in, com->fd_out, NULL, NULL));
+    }
     rc = read_all(com->fd_in, &in, &n);
     if (rc) return rc;
     /* compress_stats.bytes is an int (src/include/deflate_ext.h:20): the record stream cannot describe more */
     if (com->fd_stats >= 0 && n >= (size_t)INT_MAX) { free(in); return -E_RANGE; }
     dfl_b200_default_params(&prm);
     prm.window = com->sliding_window;
+    prm.block_mode = env_block_mode();
     cap = dfl_b200_bound(&prm, n) + 16;
     out = (unsigned char *)malloc(cap);
     if (!out) { free(in); return -E_MALLOC; }

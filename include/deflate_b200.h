@@ -148,6 +148,10 @@ int dfl_b200_set_fd_piece(dfl_ctx *ctx, size_t bytes); /* piece size of the fd p
  */
 int dfl_b200_compress_host_multi(dfl_ctx **ctxs, int ndev, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                                  size_t *out_len);
+/* The same from fd to fd (what deflate_compress() runs when DFL_B200_DEVICES names several GPUs): fd_in is read to its
+ * end into a pinned buffer that ctxs[0] keeps between calls, the stream is written to fd_out (-1: discarded). */
+int dfl_b200_compress_fd_multi(dfl_ctx **ctxs, int ndev, int fd_in, int fd_out, unsigned long long *in_bytes,
+                               unsigned long long *out_bytes);
 /* Adler-32 of a concatenation A | B from adler32(A), adler32(B) (both from start value 1) and len(B). */
 uint32_t dfl_b200_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);
 

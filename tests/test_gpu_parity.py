@@ -995,3 +995,65 @@ def test_fd_pipeline_mapped_output(D, O, tmp_path, n, piece):
     finally:
         os.close(mi), os.close(mo)
     comp.close()
+
+
+@pytest.mark.gpu
+def test_device_list_through_the_reference_entry_point(D, O, tmp_path, monkeypatch):
+    """DFL_B200_DEVICES names several devices: deflate_compress(fd_in, fd_out, -1, sw, 0) shards the input over one
+    context per entry (here all on GPU 0, plus 0,1 when there is a second GPU) and writes the stream one GPU writes;
+    regular file, memfd and pipe inputs; with a record stream asked for the call stays on the first device."""
+    import threading
+    import torch
+
+    data = make_input("markov", 17, 0, 1500001)
+    want = O.zlib_compress(data, O.params())
+    src = tmp_path / "in"
+    src.write_bytes(data.tobytes())
+    lists = ["0,0,0"] + (["0,1"] if torch.cuda.device_count() > 1 else [])
+    for devs in lists:
+        monkeypatch.setenv("DFL_B200_DEVICES", devs)
+        # regular file in, read-write file out
+        dst = tmp_path / "out.z"
+        fi, fo = os.open(src, os.O_RDONLY), os.open(dst, os.O_RDWR | os.O_CREAT | os.O_TRUNC)
+        try:
+            assert D.deflate_compress(fi, fo, -1, 32768, 0) == 0
+            assert os.lseek(fi, 0, os.SEEK_CUR) == data.size
+        finally:
+            os.close(fi), os.close(fo)
+        assert dst.read_bytes() == want, devs
+        # pipe in, memfd out
+        r_in, w_in = os.pipe()
+        mo = os.memfd_create("out")
+
+        def feed():
+            view = memoryview(data.tobytes())
+            pos = 0
+            while pos < len(view):
+                pos += os.write(w_in, view[pos:pos + (1 << 20)])
+            os.close(w_in)
+
+        t = threading.Thread(target=feed)
+        t.start()
+        try:
+            assert D.deflate_compress(r_in, mo, -1, 32768, 0) == 0
+        finally:
+            t.join()
+            os.close(r_in)
+        size = os.lseek(mo, 0, os.SEEK_CUR)
+        assert os.pread(mo, size, 0) == want, devs
+        os.close(mo)
+        # a record stream keeps the call on one device; same stream
+        fi, fo, fs = os.open(src, os.O_RDONLY), os.open(dst, os.O_WRONLY | os.O_TRUNC), os.open(tmp_path / "stats", os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        try:
+            assert D.deflate_compress(fi, fo, fs, 32768, 0) == 0
+        finally:
+            os.close(fi), os.close(fo), os.close(fs)
+        assert dst.read_bytes() == want
+    monkeypatch.delenv("DFL_B200_DEVICES")
+    # empty input on several devices
+    monkeypatch.setenv("DFL_B200_DEVICES", "0,0")
+    mi, mo = os.memfd_create("in"), os.memfd_create("out")
+    assert D.deflate_compress(mi, mo, -1, 32768, 0) == 0
+    size = os.lseek(mo, 0, os.SEEK_CUR)
+    assert os.pread(mo, size, 0) == O.zlib_compress(np.zeros(0, dtype=np.uint8), O.params())
+    os.close(mi), os.close(mo)
