@@ -619,6 +619,7 @@ def run_gpu(args) -> None:
     for _ in range(max(2, min(args.steps, 5))):
         step(0, with_gather=False)
         k_match_solo.append(comps[0].kernel_ms()["k_match"])
+    kernel_ms_solo = comps[0].kernel_ms()  # every kernel of one step, nothing else in flight
     drain()
     sync()
 
@@ -711,7 +712,10 @@ def run_gpu(args) -> None:
                        "call": "deflate_compress(memfd_in, memfd_out, -1, 32768, 0): read(2)/pread(2) + H2D + kernels + D2H + "
                                "write(2) inside, best of 3" + ("" if not fd_rc else f" (error {fd_rc})")},
             "gpu_launches": int(launches),
-            "kernel_ms_per_step": {k: v for k, v in kernel_ms.items()},
+            "kernel_ms_per_step": {k: v for k, v in kernel_ms_solo.items()},
+            "kernel_ms_per_step_what": "CUDA events around each launch, one step on one stream right after the timed region (inside the "
+                                       "timed two-stream loop the events also bracket waits for SMs: kernel_ms_in_timed_loop)",
+            "kernel_ms_in_timed_loop": {k: v for k, v in kernel_ms.items() if v},
             "roofline": {"bound": "hbm", "kernel": "k_match", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "launch_ms": km,
