@@ -144,7 +144,10 @@ def _u8(data) -> np.ndarray:
 
 
 class Compressor:
-    """One dfl_ctx (include/deflate_b200.h) bound to a CUDA device."""
+    """One dfl_ctx (include/deflate_b200.h) bound to a CUDA device.  Parameters as struct dfl_params: window (the
+    reference's `sw`), seg_bytes, chain_limit (0 = walk every chain to its end, as the reference does), use_dict,
+    block_mode (0 = cheapest of stored / fixed / dynamic per segment, 1-3 = force one, 4 = cheapest with adaptive block
+    splitting: up to 8 blocks per segment where that saves bits)."""
 
     def __init__(self, device: int = 0, window: int = 32768, seg_bytes: int = 32768, chain_limit: int = 0,
                  use_dict: int = 1, block_mode: int = 0):
