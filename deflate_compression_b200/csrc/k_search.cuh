@@ -293,7 +293,19 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                 if (c >= nchunks) {
                     st = ST_FIN;
                 } else {
-                    const int ci = c * MATCH_CHUNK;
+                    int ci = c * MATCH_CHUNK;
+#if START_AFTER_DELIM
+                    /* A chain may start anywhere in its chunk (chains only add parallelism; the one from position 0 finds
+                     * every head by itself).  Right after a delimiter -- a byte <= ' ' within the chunk's first 8 -- it is more
+                     * likely to start on a head of the true parse and merges with it a head sooner: 2 % fewer search cycles
+                     * on text and log lines, nothing on data without such bytes. */
+                    if (c && ci + 16 <= seglen) {
+                        const uint32_t w0 = ld4s(dbase + hist + ci - 1), w1 = ld4s(dbase + hist + ci + 3);
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            if ((((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFF) <= 0x20) { ci += j; break; }
+                    }
+#endif
                     const uint32_t bit = 1u << (ci & 31);
                     /* a chain that has already claimed a head inside this chunk covers it (it runs until
                      * it meets a claimed head); starting here too would only add speculative heads */
