@@ -28,6 +28,9 @@
 #ifndef START_AFTER_DELIM
 #define START_AFTER_DELIM 1 /* a speculative chain starts after the first delimiter byte of its chunk's first 8, if there is one */
 #endif
+#ifndef DELIM_MAX
+#define DELIM_MAX 0x20
+#endif
 #define SORT_WARPS 32    /* every warp sorts one stripe */
 #define SORT_BINS 128    /* 7-bit digits: bucket = digit2 * 128 + digit1 */
 #define SCRATCH_SLOTS 256

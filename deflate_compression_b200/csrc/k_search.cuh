@@ -303,7 +303,7 @@ __device__ __forceinline__ void search_segment(MatchSmem &S, const uint32_t soff
                         const uint32_t w0 = ld4s(dbase + hist + ci - 1), w1 = ld4s(dbase + hist + ci + 3);
 #pragma unroll
                         for (int j = 0; j < 8; j++)
-                            if ((((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFF) <= 0x20) { ci += j; break; }
+                            if ((((j < 4 ? w0 : w1) >> ((j & 3) * 8)) & 0xFF) <= DELIM_MAX) { ci += j; break; }
                     }
 #endif
                     const uint32_t bit = 1u << (ci & 31);
