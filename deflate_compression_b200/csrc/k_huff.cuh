@@ -352,6 +352,14 @@ k_huff(long long n, long long seg0, int nseg, dfl_params prm, SegArrays A)
 
 #define SPLIT_WARPS 2
 
+/* k_huff_split weighs and builds blocks at four places: one copy of the planner, called (inlined four times it is
+ * 62 K SASS lines and the kernel spends its time fetching instructions: 9.6 -> 6 ms on data that splits everywhere) */
+__device__ __noinline__ HuffPlan huff_plan_call(HuffSmem &S, const int lane, const unsigned long long extra, const long long nbytes,
+                                                const int block_mode, const bool cost_only)
+{
+    return huff_plan(S, lane, extra, nbytes, block_mode, cost_only);
+}
+
 /* per-block arrays of a chunk in block_mode 4 (block b of segment sl at index sl * DFL_SUB_MAX + b) */
 struct SplitArrays {
     uint32_t *nblk;                 /* [nseg] blocks of the segment; NULL = not splitting */
@@ -439,7 +447,7 @@ k_huff_split(long long n, long long seg0, int nseg, dfl_params prm, const uint32
         S.H.d_freq[lane] = lane < ND ? fd : 0u;
         ex = __reduce_add_sync(FULL, ex);
         __syncwarp();
-        return huff_plan(S.H, lane, ex, (long long)S.pos_start[b] - (long long)S.pos_start[a], prm.block_mode == 4 ? 0 : prm.block_mode, cost_only);
+        return huff_plan_call(S.H, lane, ex, (long long)S.pos_start[b] - (long long)S.pos_start[a], prm.block_mode == 4 ? 0 : prm.block_mode, cost_only);
     };
 
     /* ---- top-down bisection (explicit stack: ranges still to be looked at, leftmost on top; a range that came out of
