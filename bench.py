@@ -453,29 +453,66 @@ def run_gpu(args) -> None:
     comp = D.Compressor(device=local)
     comp.enable_timing(True)
     cap = comp.bound(n)
-    # two output buffers: the gather of step k (NCCL, its own stream) overlaps the kernels of step k + 1
-    d_outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)]
+    # output buffers in rotation: the gather of step k overlaps the kernels of step k + 1 (three when there is a gather:
+    # a shard's buffer is written again two steps after rank 0 was seen to have taken it)
+    NB = 3 if world > 1 else 2
+    d_outs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(NB)]
     d_out = d_outs[0]
     stream = torch.cuda.current_stream().cuda_stream
     is_final = rank == world - 1
 
     gather_bufs = None
     if world > 1 and rank == 0:
-        gather_bufs = [torch.empty(world * cap, dtype=torch.uint8, device=dev) for _ in range(2)]
-    pending = [None, None]
+        gather_bufs = [torch.empty(world * cap, dtype=torch.uint8, device=dev) for _ in range(NB)]
+    pending = [None] * NB
     last_gather = {}
 
+    # How the shards get to rank 0.  "nccl" (default): batched isend / irecv; its kernels take SMs from the match kernels
+    # (N = 8: 143.6 of 160.8 GB/s compress-only).  "ipc" (DFL_BENCH_GATHER=ipc): every rank opens its output buffers to
+    # rank 0 through CUDA IPC and rank 0's copy engine pulls the bytes over NVLink on a stream of its own -- no SM taken,
+    # but one copy stream does not carry seven shards a step: measured 40.2 against 41.2 GB/s at N = 2 and 81 against 144
+    # at N = 8, so it stays an option.  Falls back to "nccl" when the buffers cannot be opened.
+    gather_mode = os.environ.get("DFL_BENCH_GATHER", "nccl") if world > 1 else "none"
+    peer_bufs, copy_stream, prev_copy = None, None, [None]
+    if gather_mode == "ipc":
+        ok = 1
+        mine = None
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+
+            mine = [reduce_tensor(t) for t in d_outs]
+        except Exception:
+            ok = 0
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        if rank == 0 and ok:
+            try:
+                peer_bufs = {r: [fn(*a) for fn, a in handles[r]] for r in range(1, world)}
+                copy_stream = torch.cuda.Stream(device=dev)
+                torch.cuda.set_device(local)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            gather_mode, peer_bufs = "nccl", None
+
     def drain(b=None):
-        """Buffer b's transfer (or both) has landed, as far as buffer b's stream is concerned; drain() without an
-        argument also joins the second stream into the current one, where the clock's events are recorded."""
-        for k in ((0, 1) if b is None else (b,)):
+        """Output buffer b's transfer (or every buffer's) has landed; drain() without an argument also joins the second
+        stream into the current one, where the clock's events are recorded."""
+        for k in (range(NB) if b is None else (b,)):
             if pending[k] is not None:
-                with torch.cuda.stream(tstreams[k]):
-                    for q in pending[k]:
-                        q.wait()
+                if gather_mode == "ipc":
+                    pending[k].synchronize()
+                else:
+                    with torch.cuda.stream(tstreams[k & 1]):
+                        for q in pending[k]:
+                            q.wait()
                 pending[k] = None
         if b is None:
             torch.cuda.current_stream().wait_stream(tstreams[1])
+            if copy_stream is not None:
+                torch.cuda.current_stream().wait_stream(copy_stream)
 
     # two contexts on two streams take the steps in turn (a context has one call in flight): step k + 1's kernels are
     # already enqueued while the host reads step k's size back -- and, for N > 1, exchanges the sizes and posts the transfer
@@ -485,16 +522,20 @@ def run_gpu(args) -> None:
         c.enable_timing(True)
 
     def launch(i: int):
-        b = i & 1
-        drain(b)
-        comps[b].enqueue(d_in, n, hist, is_final, d_outs[b].data_ptr(), cap, tstreams[b].cuda_stream)
+        b, ob = i & 1, i % NB
+        drain(ob)
+        comps[b].enqueue(d_in, n, hist, is_final, d_outs[ob].data_ptr(), cap, tstreams[b].cuda_stream)
 
     def collect(i: int, with_gather: bool = True):
         """Sizes of step i (its kernels are done), then the gather of sizes and bytes to rank 0; the transfer itself is
         left in flight and is waited for before its buffers are used again, or by drain()."""
-        b = i & 1
+        b, ob = i & 1, i % NB
         out_len, adler = comps[b].finish(tstreams[b].cuda_stream)
         if world > 1 and with_gather:
+            if gather_mode == "ipc" and rank == 0 and prev_copy[0] is not None:
+                # rank 0 joins the exchange of sizes only once it has taken the step before: the others read that as
+                # "the buffer of two steps ago is free" (they write it again one step from now)
+                prev_copy[0].synchronize()
             with torch.cuda.stream(tstreams[b]):
                 sizes = torch.zeros(2 * world, dtype=torch.int64, device=dev)
                 mine = torch.tensor([out_len, adler], dtype=torch.int64, device=dev)
@@ -503,13 +544,24 @@ def run_gpu(args) -> None:
                 sz = meta[0::2]
                 if rank == 0:
                     offs = np.concatenate([[0], np.cumsum(sz)])
-                    gbuf = gather_bufs[b]
-                    gbuf[:sz[0]].copy_(d_outs[b][:sz[0]])
-                    ops = [dist.P2POp(dist.irecv, gbuf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
-                    pending[b] = dist.batch_isend_irecv(ops)
-                    last_gather.update(buf=b, sizes=sz, adlers=meta[1::2])
-                else:
-                    pending[b] = dist.batch_isend_irecv([dist.P2POp(dist.isend, d_outs[b][:out_len], 0)])
+                    gbuf = gather_bufs[ob]
+                    if gather_mode == "ipc":
+                        cs = copy_stream.cuda_stream
+                        L = D.lib()
+                        L.dfl_b200_copy_async(gbuf.data_ptr(), d_outs[ob].data_ptr(), sz[0], cs)
+                        for r in range(1, world):
+                            L.dfl_b200_copy_async(gbuf.data_ptr() + int(offs[r]), peer_bufs[r][ob].data_ptr(), sz[r], cs)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        pending[ob] = ev
+                        prev_copy[0] = ev
+                    else:
+                        gbuf[:sz[0]].copy_(d_outs[ob][:sz[0]])
+                        ops = [dist.P2POp(dist.irecv, gbuf[int(offs[r]):int(offs[r]) + sz[r]], r) for r in range(1, world)]
+                        pending[ob] = dist.batch_isend_irecv(ops)
+                    last_gather.update(buf=ob, sizes=sz, adlers=meta[1::2])
+                elif gather_mode != "ipc":
+                    pending[ob] = dist.batch_isend_irecv([dist.P2POp(dist.isend, d_outs[ob][:out_len], 0)])
         return out_len, adler
 
     def step(i: int = 0, with_gather: bool = True):
@@ -557,7 +609,7 @@ def run_gpu(args) -> None:
     launches = sum(c.kernel_launches() for c in comps) - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     kernel_ms = comps[(args.steps - 1) & 1].kernel_ms()
-    timed_out = d_outs[(args.steps - 1) & 1]  # the buffer the last timed step wrote
+    timed_out = d_outs[(args.steps - 1) % NB]  # the buffer the last timed step wrote
 
     # ---- what the timed loop produced, checked outside the timed region ----
     import hashlib
@@ -700,6 +752,8 @@ def run_gpu(args) -> None:
             "config": {"workload": "256 MiB order-2 Markov text per GPU (BASELINE configs[1], seed 2, 32 MiB stripes)",
                        "window": WINDOW, "segment_bytes": 32768, "chain_limit": 0, "block_mode": "cheapest (all dynamic)",
                        "l2": "inputs larger than L2 (256 MiB per step)", "steps_overlap": "two contexts on two streams take the steps in turn; step k + 1 is enqueued while step k's size is read back", "sharding": f"contiguous, {world} rank(s)",
+                       "gather": {"ipc": "rank 0's copy engine pulls every shard's bytes out of buffers opened through CUDA IPC (no SMs)",
+                                  "nccl": "batched NCCL isend / irecv to rank 0", "none": "single GPU"}[gather_mode],
                        "cpu_binding": binding},
             "compression_ratio": n_total / out_total,
             "roundtrip_ok": roundtrip_ok,

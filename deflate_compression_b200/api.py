@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         L.dfl_b200_compress_host_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.dfl_b200_adler32_combine.restype = C.c_uint32
         L.dfl_b200_adler32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+        L.dfl_b200_copy_async.argtypes = [vp, vp, C.c_size_t, vp]
         L.dfl_b200_kernel_launches.restype = C.c_long
         L.dfl_b200_kernel_launches.argtypes = [vp]
         L.dfl_b200_enable_timing.argtypes = [vp, C.c_int]

@@ -718,3 +718,10 @@ extern "C" int dfl_b200_compress_fd_multi(dfl_ctx **ctxs, int ndev, int fd_in, i
     if (out_bytes) *out_bytes = total_out;
     return DFL_OK;
 }
+
+extern "C" int dfl_b200_copy_async(void *dst, const void *src, size_t n, void *stream)
+{
+    dfl_ctx *ctx = NULL;
+    if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, (cudaStream_t)stream));
+    return DFL_OK;
+}

@@ -152,6 +152,11 @@ int dfl_b200_compress_host_multi(dfl_ctx **ctxs, int ndev, const uint8_t *in, si
  * end into a pinned buffer that ctxs[0] keeps between calls, the stream is written to fd_out (-1: discarded). */
 int dfl_b200_compress_fd_multi(dfl_ctx **ctxs, int ndev, int fd_in, int fd_out, unsigned long long *in_bytes,
                                unsigned long long *out_bytes);
+
+/* cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, stream): a copy between any two addresses of the unified address
+ * space -- e.g. from another GPU's buffer opened through CUDA IPC -- done by the copy engine of the stream's device, no
+ * SM involved.  bench.py gathers the ranks' compressed shards on rank 0 with it while the next step's kernels run. */
+int dfl_b200_copy_async(void *dst, const void *src, size_t n, void *stream);
 /* Adler-32 of a concatenation A | B from adler32(A), adler32(B) (both from start value 1) and len(B). */
 uint32_t dfl_b200_adler32_combine(uint32_t a1, uint32_t a2, uint64_t len2);
 
